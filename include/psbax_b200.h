@@ -1,0 +1,152 @@
+/* psbax_b200.h — C ABI of the B200-native PS-BAX sample-path library.
+ *
+ * One shared object (psbax_b200/libpsbax_b200.so, sm_100a) that evaluates S GP
+ * posterior sample paths over a candidate set X* [N, d] and runs the BAX
+ * algorithm reduction on every path in the same pass:
+ *
+ *   f_s(x) = y_mean + y_std * ( mean_const
+ *                              + sum_l W[s,l] * cos(omega[g,l,:] . x + bias[g,l])
+ *                              + sum_j V[s,j] * kappa(|| x*inv_ls - Xtrain[j] ||) )
+ *
+ * g = 0 when G == 1 (shared basis, Matheron/north-star form), g = s when G == S
+ * (one basis per sample: the reference's botorch `get_gp_samples` form).
+ *
+ * The reference has no FFI: the interface replaced is the Python callable
+ * protocol of /root/reference.  Each entry point cites the
+ * reference code whose work it takes over.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative PSBAX_E_* code otherwise and
+ *    never throws; psbax_last_error() gives the message of the calling thread's
+ *    last failure;
+ *  - the caller owns every buffer; all pointers in psbax_paths_t and all data
+ *    arguments are DEVICE pointers (fp32, row-major, contiguous) unless stated;
+ *    nothing is allocated after psbax_pack_bytes()/psbax_workspace_bytes();
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *    calls are asynchronous with respect to the host;
+ *  - re-entrant: no global mutable state besides per-device function attributes.
+ */
+#ifndef PSBAX_B200_H
+#define PSBAX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSBAX_ABI_VERSION 1
+
+enum {
+  PSBAX_OK = 0,
+  PSBAX_E_INVALID = -1,     /* bad argument / inconsistent shapes */
+  PSBAX_E_UNSUPPORTED = -2, /* shape outside what the kernels are built for */
+  PSBAX_E_CUDA = -3,        /* a CUDA runtime call failed */
+  PSBAX_E_WORKSPACE = -4    /* pack / workspace buffer too small */
+};
+
+enum { /* psbax_paths_t.kernel */
+  PSBAX_KERNEL_RBF = 0,
+  PSBAX_KERNEL_MATERN12 = 1,
+  PSBAX_KERNEL_MATERN32 = 2,
+  PSBAX_KERNEL_MATERN52 = 3
+};
+
+enum { /* psbax_paths_t.engine: which kernel family evaluates a shared basis */
+  PSBAX_ENGINE_AUTO = 0,
+  PSBAX_ENGINE_SIMT = 1,   /* FFMA + MUFU kernels */
+  PSBAX_ENGINE_TENSOR = 2  /* tcgen05 3xTF32 kernel (G == 1 only) */
+};
+
+/* The S sample paths.  Replaces the closure `get_gp_samples` returns
+ * (src/utils.py:222-229; botorch 0.10 gp_sampling.get_deterministic_model). */
+typedef struct psbax_paths {
+  int32_t d;       /* input dimension                                         */
+  int32_t L;       /* RFF features per basis (reference: 1000, utils.py:227)   */
+  int32_t G;       /* number of bases: 1 (shared) or S (one per sample)        */
+  int32_t S;       /* number of sample paths                                   */
+  int32_t n;       /* training points in the exact-kernel update (0 = none)    */
+  int32_t kernel;  /* PSBAX_KERNEL_*                                           */
+  int32_t engine;  /* PSBAX_ENGINE_*                                           */
+  int32_t reserved;
+  const float* omega;   /* [G, L, d]  frequencies / lengthscale                */
+  const float* bias;    /* [G, L]     phases in [0, 2pi)                       */
+  const float* W;       /* [S, L]     weights * sqrt(2*outputscale/L)          */
+  const float* Xtrain;  /* [n, d]     training inputs / lengthscale            */
+  const float* inv_ls;  /* [d]        1 / lengthscale                          */
+  const float* V;       /* [S, n]     kernel-update weights * outputscale      */
+  float mean_const;     /* GP constant mean (standardized units)               */
+  float y_mean;         /* Standardize.means  (fit_model.py:43)                */
+  float y_std;          /* Standardize.stdvs                                   */
+  float reserved_f;
+} psbax_paths_t;
+
+int psbax_version(void);
+
+/* Copies the calling thread's last error message (NUL-terminated) into buf. */
+int psbax_last_error(char* buf, size_t len);
+
+/* Number of SMs of the current device (sizes persistent grids / workspaces). */
+int psbax_device_sms(int* sms);
+
+/* Size of, and construction of, the device-side operand pack for one batch of
+ * paths: feature tables padded/interleaved for coalesced staging, [W;V] stacked
+ * K-major, and (tensor engine) the hi/lo TF32 split of [W;V] in UMMA layout.
+ * Build once per draw, reuse for every evaluation. */
+int psbax_pack_bytes(const psbax_paths_t* paths, size_t* bytes);
+int psbax_pack(const psbax_paths_t* paths, void* pack, size_t pack_bytes, void* stream);
+
+/* Scratch needed by the fused reductions (per-CTA partial results). */
+int psbax_workspace_bytes(const psbax_paths_t* paths, int64_t N, int32_t k, size_t* bytes);
+
+/* out[i, s] = f_s(X[i, :]), out is [N, ld_out] with ld_out >= S.
+ * Replaces PosteriorMean(sample).forward / eval_gp_sample (a4) and the
+ * chunk-of-100 loop eval_in_batch (src/algorithms/topk.py:48-49). */
+int psbax_eval_values(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                      float* out, int64_t ld_out, void* stream);
+
+/* Fused evaluation + LevelSetEstimator reduction (src/algorithms/levelset.py:34-39)
+ * for all S paths: mask bit (i % 32) of mask[s, i / 32] = (f_s(X[i]) > tau);
+ * count[s] = popcount; maxval/argmax[s] = max and (smallest) arg max of f_s over
+ * the N rows, argmax reported as row_offset + i (the empty-set fallback
+ * `[argmax fx]`).  mask may be NULL (argmax / ES-population scoring only);
+ * mask_ld >= ceil(N/32) words per sample. */
+int psbax_eval_levelset(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                        int64_t row_offset, float tau, uint32_t* mask, int64_t mask_ld,
+                        int64_t* count, float* maxval, int64_t* argmax, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* Fused evaluation + TopK reduction (src/algorithms/topk.py:31-34) for all S
+ * paths: out_val[s, 0..k) the k largest f_s values, largest first, ties broken
+ * towards the smaller index; out_idx[s, j] = row_offset + row.  1 <= k <= 64,
+ * k <= N. */
+int psbax_eval_topk(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                    int64_t row_offset, int32_t k, float* out_val, int64_t* out_idx,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Merge `lists` sorted top-k lists per sample (in_val/in_idx are
+ * [lists, S, k]) into one [S, k] list; the step after the all-gather of the
+ * per-GPU shard results.  Unused slots carry -inf / -1. */
+int psbax_topk_merge(const float* in_val, const int64_t* in_idx, int32_t lists, int32_t S,
+                     int32_t k, float* out_val, int64_t* out_idx, void* stream);
+
+/* DiscoBAX SubsetSelect reduction (src/algorithms/discobax.py:37-56) for S
+ * paths at once: values[b, i] = fx[i, s] + etas[b, i] (optionally max(0, .)),
+ * first pick = arg max of the column means, then k-1 greedy picks maximising
+ * mean_b max(cur_max[b], values[b, j]); already-chosen j score 0; ties to the
+ * smaller index.  fx is [N, ld_fx] as written by psbax_eval_values, etas is
+ * [B, N], out_idx is [S, k] (int64). */
+int psbax_subset_select(const float* fx, int64_t ld_fx, const float* etas, int64_t N, int32_t B,
+                        int32_t S, int32_t k, int32_t nonneg, int64_t* out_idx, void* stream);
+
+/* grad[i, :] = d f_{s_i}(X[i, :]) / dx and val[i] = f_{s_i}(X[i, :]) for a list of
+ * (point, sample) pairs: what LBFGSB obtains through autograd
+ * (src/algorithms/lbfgsb.py:29-39).  sample_idx is int32 [N] (NULL = sample 0). */
+int psbax_eval_grad(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                    const int32_t* sample_idx, float* val, float* grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSBAX_B200_H */

@@ -1,0 +1,2 @@
+from .entropy import EntropyAcquisitionFunction  # noqa: F401
+from .posterior_sampling import gen_posterior_sampling_batch  # noqa: F401

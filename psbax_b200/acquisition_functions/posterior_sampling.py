@@ -1,0 +1,42 @@
+"""PS-BAX acquisition (``/root/reference/src/acquisition_functions/posterior_sampling.py:46-83``).
+
+The reference draws ``batch_size`` sample paths one after another and runs the algorithm on
+each in Python chunks of 100 candidates.  Here all paths are drawn together and the
+algorithm runs on the whole batch in one fused GPU launch; pooling and the max-entropy pick
+are unchanged.
+"""
+import math
+
+import torch
+
+from ..utils import get_function_sample_batch
+from .entropy import EntropyAcquisitionFunction, optimize_acqf_discrete
+
+
+def gen_posterior_sampling_batch(model, algorithm, batch_size, **kwargs):
+    if algorithm.params.name == "SubsetSelect":
+        # at least batch_size labels: ceil(batch_size / k) paths (posterior_sampling.py:51-54)
+        k = algorithm.params.k
+        num_paths = max(1, math.ceil(batch_size / k))
+        paths = get_function_sample_batch(model, num_paths, **kwargs)
+        batch = []
+        for labels in algorithm.execute_batch(paths):
+            batch.extend(labels)
+        x_batch = algorithm.index_to_x(batch)
+        acq_func = EntropyAcquisitionFunction(model=model)
+        x_next, _ = optimize_acqf_discrete(acq_function=acq_func, q=batch_size, choices=x_batch,
+                                           max_batch_size=100)
+        return algorithm.obj_func.get_idx_from_x(x_next)
+
+    paths = get_function_sample_batch(model, batch_size, **kwargs)
+    rows = []
+    for x_output in algorithm.execute_batch(paths):
+        x_output = torch.as_tensor(x_output)
+        if x_output.dim() == 1:
+            x_output = x_output.reshape(1, -1)
+        rows.append(x_output)
+    x_batch = torch.cat(rows)  # pooled outputs of all paths, duplicates kept
+    acq_func = EntropyAcquisitionFunction(model=model)
+    x_next, _ = optimize_acqf_discrete(acq_function=acq_func, q=batch_size, choices=x_batch,
+                                       max_batch_size=100)
+    return x_next

@@ -1,0 +1,86 @@
+"""Level-set BAX algorithm (interface and results of
+``/root/reference/src/algorithms/levelset.py:10-56``)."""
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+from ..sample_paths import SamplePath, SamplePathBatch
+from .algorithm import Algorithm, eval_in_batch
+
+
+class LevelSetEstimator(Algorithm):
+    def set_params(self, params):
+        super().set_params(params)
+        self.params.name = params.get("name", "SimpleLevelSet")
+        self.params.threshold = params.get("threshold", 10)
+        self.params.x_set = params.get("x_set", None)  # numpy [N, d], as in the reference
+        self.params.no_copy = params.get("no_copy", None)
+        self._dev_x = None
+
+    def initialize(self):
+        self.exe_path = Namespace()
+
+    def device_candidates(self, device) -> torch.Tensor:
+        if self._dev_x is None or self._dev_x.device != torch.device(device):
+            self._dev_x = torch.as_tensor(self.params.x_set).to(device, torch.float32).contiguous()
+        return self._dev_x
+
+    def _finish(self, idx, fx_at_idx):
+        x_set = self.params.x_set
+        self.exe_path.idx = list(idx)
+        self.exe_path.x = np.atleast_2d(np.asarray(x_set)[idx])
+        self.exe_path.y = np.atleast_1d(fx_at_idx)
+        return self.exe_path, self.exe_path.x
+
+    def _from_values(self, fx: np.ndarray):
+        idx = np.where(fx > self.params.threshold)[0]
+        if len(idx) == 0:  # empty super-level set -> the arg max (levelset.py:35-37)
+            idx = np.array([int(np.argmax(fx))])
+        return self._finish(idx, fx[idx])
+
+    def _from_result(self, res, s, y_of):
+        idx = res.indices(s).cpu().numpy()
+        return self._finish(idx, y_of(idx))
+
+    def run_algorithm_on_f(self, f):
+        self.initialize()
+        if isinstance(f, SamplePathBatch):
+            if f.S != 1:
+                raise ValueError("run_algorithm_on_f takes one path; use run_algorithm_on_batch")
+            f = f.path(0)
+        if isinstance(f, SamplePath):
+            batch = f._one()
+            X = self.device_candidates(batch.device)
+            res = batch.levelset(X, self.params.threshold)
+            idx = res.indices(0)
+            y = batch.values(X[idx])[:, 0].double().cpu().numpy()
+            return self._finish(idx.cpu().numpy(), y)
+        if getattr(f, "expects_q_dim", False):
+            x_set = torch.from_numpy(np.asarray(self.params.x_set)).unsqueeze(1)
+            fx = eval_in_batch(f, x_set).detach().numpy().flatten()
+        else:
+            fx = np.asarray(f(self.params.x_set)).flatten()
+        return self._from_values(fx)
+
+    def run_algorithm_on_batch(self, paths: SamplePathBatch, with_values: bool = True):
+        """One fused launch for all S paths -> [(exe_path, output)] in sample order."""
+        X = self.device_candidates(paths.device)
+        res = paths.levelset(X, self.params.threshold)
+        results = []
+        for s in range(paths.S):
+            self.initialize()
+            idx = res.indices(s)
+            if with_values:
+                y = paths.path(s)._one().values(X[idx])[:, 0].double().cpu().numpy()
+            else:
+                y = np.full(idx.numel(), np.nan)
+            results.append(self._finish(idx.cpu().numpy(), y))
+        return results
+
+    def execute(self, f):
+        self.run_algorithm_on_f(f)
+        return self.exe_path.x
+
+    def get_output(self):
+        return self.exe_path.x

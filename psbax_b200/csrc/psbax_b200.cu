@@ -1,0 +1,386 @@
+// C-ABI entry points of libpsbax_b200.so (declared in include/psbax_b200.h).
+// Host side: argument validation, operand-pack layout, launch configuration.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "sp_common.cuh"
+#include "sp_extra.cuh"
+#include "sp_simt.cuh"
+#include "sp_tensor.cuh"
+
+using namespace psbax;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      return fail(PSBAX_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+int device_sms(int* sms) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev));
+  return PSBAX_OK;
+}
+
+int validate(const psbax_paths_t* p) {
+  if (!p) return fail(PSBAX_E_INVALID, "paths is NULL");
+  if (p->d < 1 || p->d > 1024) return fail(PSBAX_E_INVALID, "d=%d out of range [1,1024]", p->d);
+  if (p->S < 1) return fail(PSBAX_E_INVALID, "S=%d must be >= 1", p->S);
+  if (p->L < 0 || p->n < 0) return fail(PSBAX_E_INVALID, "L=%d, n=%d must be >= 0", p->L, p->n);
+  if (p->L + p->n < 1) return fail(PSBAX_E_INVALID, "L + n must be >= 1");
+  if (p->G != 1 && p->G != p->S)
+    return fail(PSBAX_E_INVALID, "G=%d must be 1 (shared basis) or S=%d", p->G, p->S);
+  if (p->kernel < PSBAX_KERNEL_RBF || p->kernel > PSBAX_KERNEL_MATERN52)
+    return fail(PSBAX_E_INVALID, "unknown kernel id %d", p->kernel);
+  if (p->L > 0 && (!p->omega || !p->bias || !p->W))
+    return fail(PSBAX_E_INVALID, "omega / bias / W must be non-NULL when L > 0");
+  if (p->n > 0 && (!p->Xtrain || !p->inv_ls || !p->V))
+    return fail(PSBAX_E_INVALID, "Xtrain / inv_ls / V must be non-NULL when n > 0");
+  if (p->engine < PSBAX_ENGINE_AUTO || p->engine > PSBAX_ENGINE_TENSOR)
+    return fail(PSBAX_E_INVALID, "unknown engine id %d", p->engine);
+  if (p->engine == PSBAX_ENGINE_TENSOR && !tensor_supported(p))
+    return fail(PSBAX_E_UNSUPPORTED,
+                "tensor engine needs a shared basis (G == 1), d <= %d and S <= %d (got G=%d d=%d S=%d)",
+                TC_MAX_D, TC_MAX_S, p->G, p->d, p->S);
+  return PSBAX_OK;
+}
+
+Layout make_layout(const psbax_paths_t* p) {
+  Layout l{};
+  l.d = p->d; l.L = p->L; l.G = p->G; l.S = p->S; l.n = p->n; l.kernel = p->kernel;
+  l.dp4 = (p->d <= 2) ? 2 : round_up(p->d, 4);
+  l.OS = round_up(l.dp4 + 1, 4);
+  l.OSB = round_up(l.dp4 + 2, 4);
+  l.Lp = round_up(p->L, 8);
+  l.np_ = round_up(p->n, 8);
+  l.Sp = round_up(p->S, TN);
+  const bool shared = (p->G == 1) && (p->S >= 16) && (p->L > 0);
+  if (!shared) l.mode = MODE_PERSAMPLE;
+  else if (p->engine == PSBAX_ENGINE_TENSOR || (p->engine == PSBAX_ENGINE_AUTO && tensor_supported(p)))
+    l.mode = MODE_TENSOR;
+  else l.mode = MODE_SHARED_SIMT;
+  l.Lp_ft = (l.mode == MODE_PERSAMPLE) ? 0 : l.Lp;
+  l.Kp = round_up(l.Lp_ft + l.np_, TK);
+  size_t off = 0;
+  l.off_invls = off; off += round_up(l.dp4, 4);
+  l.off_ft = off;    off += (size_t)l.Kp * l.OS;
+  l.off_wv = off;    off += (size_t)l.Kp * l.Sp;
+  l.off_pb = off;    if (l.mode == MODE_PERSAMPLE) off += (size_t)l.S * l.Lp * l.OSB;
+  off = (off + 63) / 64 * 64;  // 256-byte alignment for the tensor operands
+  l.off_tc = off;    if (l.mode == MODE_TENSOR) off += tensor_pack_floats(l);
+  l.total_floats = off;
+  return l;
+}
+
+// persistent grid: gx CTAs over the row tiles, gy sample chunks
+void grid_for(const Layout& l, long long N, int sms, int* gx, int* gy, int* ntiles) {
+  const long long nt = (N + TM - 1) / TM;
+  *ntiles = (int)nt;
+  *gy = l.Sp / TN;
+  long long want = (2LL * sms + *gy - 1) / *gy;
+  if (want < 1) want = 1;
+  long long g = nt < want ? nt : want;
+  if (g < 1) g = 1;
+  const long long tpc = (nt + g - 1) / g;
+  g = (nt + tpc - 1) / (tpc > 0 ? tpc : 1);
+  if (g < 1) g = 1;
+  *gx = (int)g;
+}
+
+size_t simt_smem_bytes(const Layout& l, int epi, int k, bool shared, bool generic) {
+  size_t state = round_up((int)epi_smem_floats(epi, k), 4);
+  size_t tile = (size_t)TN * OUT_LD;
+  if (shared) {
+    size_t work = (size_t)TK * TM + (size_t)TK * TN + (size_t)TK * l.OS + round_up(l.dp4, 4) +
+                  (generic ? (size_t)l.dp4 * TM : 0);
+    if (work > tile) tile = work;
+  } else {
+    tile += round_up(l.dp4, 4) + (generic ? (size_t)l.dp4 * TM : 0);
+  }
+  return (state + tile) * sizeof(float);
+}
+
+template <typename K>
+int launch_simt(K kern, const KArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+  if (smem > 227 * 1024) return fail(PSBAX_E_UNSUPPORTED, "shared memory %zu B exceeds 227 KB (d too large)", smem);
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, NTHREADS, smem, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return PSBAX_OK;
+}
+
+template <int EPI>
+int dispatch_simt(const KArgs& a, dim3 grid, cudaStream_t st) {
+  const Layout& l = a.lay;
+  const bool shared = l.mode != MODE_PERSAMPLE;
+  if (shared) {
+    switch (l.dp4) {
+      case 2:  return launch_simt(k_shared_simt<2, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, false), st);
+      case 4:  return launch_simt(k_shared_simt<4, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, false), st);
+      case 8:  return launch_simt(k_shared_simt<8, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, false), st);
+      case 12: return launch_simt(k_shared_simt<12, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, false), st);
+      case 16: return launch_simt(k_shared_simt<16, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, false), st);
+      default: return launch_simt(k_shared_simt<0, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, true), st);
+    }
+  }
+  switch (l.dp4) {
+    case 2:  return launch_simt(k_persample<2, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, false, false), st);
+    case 4:  return launch_simt(k_persample<4, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, false, false), st);
+    case 8:  return launch_simt(k_persample<8, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, false, false), st);
+    default: return launch_simt(k_persample<0, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, false, true), st);
+  }
+}
+
+struct Prepared {
+  KArgs a;
+  dim3 grid;
+  int sms;
+};
+
+int prepare(const psbax_paths_t* p, const void* pack, const float* X, int64_t N, Prepared* out) {
+  int rc = validate(p);
+  if (rc) return rc;
+  if (!pack) return fail(PSBAX_E_INVALID, "pack is NULL (call psbax_pack first)");
+  if (!X) return fail(PSBAX_E_INVALID, "X is NULL");
+  if (N < 1) return fail(PSBAX_E_INVALID, "N=%lld must be >= 1", (long long)N);
+  if (N > 2147483647LL - TM) return fail(PSBAX_E_UNSUPPORTED, "N=%lld exceeds 2^31 rows per call; shard the candidate set", (long long)N);
+  rc = device_sms(&out->sms);
+  if (rc) return rc;
+  KArgs& a = out->a;
+  memset(&a, 0, sizeof(a));
+  a.lay = make_layout(p);
+  a.pack = static_cast<const float*>(pack);
+  a.X = X;
+  a.N = N;
+  a.ystd = p->y_std;
+  a.c0 = (float)((double)p->y_std * (double)p->mean_const + (double)p->y_mean);
+  int gx, gy, nt;
+  grid_for(a.lay, N, out->sms, &gx, &gy, &nt);
+  a.ntiles = nt;
+  out->grid = dim3(gx, gy, 1);
+  return PSBAX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int psbax_version(void) { return PSBAX_ABI_VERSION; }
+
+int psbax_last_error(char* buf, size_t len) {
+  if (!buf || len == 0) return PSBAX_E_INVALID;
+  strncpy(buf, g_err, len - 1);
+  buf[len - 1] = 0;
+  return PSBAX_OK;
+}
+
+int psbax_device_sms(int* sms) {
+  if (!sms) return fail(PSBAX_E_INVALID, "sms is NULL");
+  return device_sms(sms);
+}
+
+int psbax_pack_bytes(const psbax_paths_t* paths, size_t* bytes) {
+  int rc = validate(paths);
+  if (rc) return rc;
+  if (!bytes) return fail(PSBAX_E_INVALID, "bytes is NULL");
+  *bytes = make_layout(paths).total_floats * sizeof(float);
+  return PSBAX_OK;
+}
+
+int psbax_pack(const psbax_paths_t* paths, void* pack, size_t pack_bytes, void* stream) {
+  int rc = validate(paths);
+  if (rc) return rc;
+  if (!pack) return fail(PSBAX_E_INVALID, "pack is NULL");
+  const Layout l = make_layout(paths);
+  if (pack_bytes < l.total_floats * sizeof(float))
+    return fail(PSBAX_E_WORKSPACE, "pack buffer too small: %zu < %zu bytes", pack_bytes,
+                l.total_floats * sizeof(float));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_pack<<<296, 256, 0, st>>>(l, paths->omega, paths->bias, paths->W, paths->Xtrain,
+                              paths->inv_ls, paths->V, static_cast<float*>(pack));
+  CUDA_TRY(cudaGetLastError());
+  if (l.mode == MODE_TENSOR) {
+    rc = tensor_pack(l, static_cast<float*>(pack), st);
+    if (rc) return fail(rc, "tensor operand pack failed");
+  }
+  return PSBAX_OK;
+}
+
+int psbax_workspace_bytes(const psbax_paths_t* paths, int64_t N, int32_t k, size_t* bytes) {
+  int rc = validate(paths);
+  if (rc) return rc;
+  if (!bytes) return fail(PSBAX_E_INVALID, "bytes is NULL");
+  if (N < 1) return fail(PSBAX_E_INVALID, "N must be >= 1");
+  if (k < 0 || k > KMAX) return fail(PSBAX_E_UNSUPPORTED, "k=%d outside [0,%d]", k, KMAX);
+  int sms = 0;
+  rc = device_sms(&sms);
+  if (rc) return rc;
+  const Layout l = make_layout(paths);
+  int gx, gy, nt;
+  grid_for(l, N, sms, &gx, &gy, &nt);
+  if (l.mode == MODE_TENSOR) gx = tensor_parts(l, N, sms);
+  const size_t per = (size_t)gx * l.Sp;
+  const size_t ls = per * (sizeof(unsigned int) + sizeof(float) + sizeof(int));
+  const size_t tk = per * (size_t)(k > 0 ? k : 1) * (sizeof(float) + sizeof(int));
+  *bytes = (ls > tk ? ls : tk) + 256;
+  return PSBAX_OK;
+}
+
+int psbax_eval_values(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                      float* out, int64_t ld_out, void* stream) {
+  Prepared pr;
+  int rc = prepare(paths, pack, X, N, &pr);
+  if (rc) return rc;
+  if (!out) return fail(PSBAX_E_INVALID, "out is NULL");
+  if (ld_out < paths->S) return fail(PSBAX_E_INVALID, "ld_out=%lld < S=%d", (long long)ld_out, paths->S);
+  pr.a.out = out;
+  pr.a.ld_out = ld_out;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pr.a.lay.mode == MODE_TENSOR) return tensor_launch(EPI_VALUES, pr.a, pr.sms, st, g_err, sizeof(g_err));
+  return dispatch_simt<EPI_VALUES>(pr.a, pr.grid, st);
+}
+
+int psbax_eval_levelset(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                        int64_t row_offset, float tau, uint32_t* mask, int64_t mask_ld,
+                        int64_t* count, float* maxval, int64_t* argmax, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  Prepared pr;
+  int rc = prepare(paths, pack, X, N, &pr);
+  if (rc) return rc;
+  if (mask && mask_ld < (N + 31) / 32)
+    return fail(PSBAX_E_INVALID, "mask_ld=%lld < ceil(N/32)=%lld", (long long)mask_ld, (long long)((N + 31) / 32));
+  size_t need = 0;
+  rc = psbax_workspace_bytes(paths, N, 0, &need);
+  if (rc) return rc;
+  if (!workspace || workspace_bytes < need)
+    return fail(PSBAX_E_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  KArgs& a = pr.a;
+  const Layout& l = a.lay;
+  const int parts = (l.mode == MODE_TENSOR) ? tensor_parts(l, N, pr.sms) : (int)pr.grid.x;
+  const size_t per = (size_t)parts * l.Sp;
+  a.row_offset = row_offset;
+  a.tau = tau;
+  a.mask = mask;
+  a.mask_ld = mask_ld;
+  a.p_cnt = static_cast<unsigned int*>(workspace);
+  a.p_max = reinterpret_cast<float*>(a.p_cnt + per);
+  a.p_arg = reinterpret_cast<int*>(a.p_max + per);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (l.mode == MODE_TENSOR) rc = tensor_launch(EPI_LEVELSET, a, pr.sms, st, g_err, sizeof(g_err));
+  else rc = dispatch_simt<EPI_LEVELSET>(a, pr.grid, st);
+  if (rc) return rc;
+  k_levelset_finalize<<<(l.S + 127) / 128, 128, 0, st>>>(a.p_cnt, a.p_max, a.p_arg, parts, l.Sp, l.S,
+                                                       row_offset, reinterpret_cast<long long*>(count),
+                                                       maxval, reinterpret_cast<long long*>(argmax));
+  CUDA_TRY(cudaGetLastError());
+  return PSBAX_OK;
+}
+
+int psbax_eval_topk(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                    int64_t row_offset, int32_t k, float* out_val, int64_t* out_idx,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  Prepared pr;
+  int rc = prepare(paths, pack, X, N, &pr);
+  if (rc) return rc;
+  if (k < 1 || k > KMAX) return fail(PSBAX_E_UNSUPPORTED, "k=%d outside [1,%d]", k, KMAX);
+  if (k > N) return fail(PSBAX_E_INVALID, "k=%d > N=%lld (torch.topk raises too)", k, (long long)N);
+  if (!out_val || !out_idx) return fail(PSBAX_E_INVALID, "out_val / out_idx is NULL");
+  size_t need = 0;
+  rc = psbax_workspace_bytes(paths, N, k, &need);
+  if (rc) return rc;
+  if (!workspace || workspace_bytes < need)
+    return fail(PSBAX_E_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  KArgs& a = pr.a;
+  const Layout& l = a.lay;
+  const int parts = (l.mode == MODE_TENSOR) ? tensor_parts(l, N, pr.sms) : (int)pr.grid.x;
+  const size_t per = (size_t)parts * l.Sp * k;
+  a.row_offset = row_offset;
+  a.k = k;
+  a.p_tv = static_cast<float*>(workspace);
+  a.p_ti = reinterpret_cast<int*>(a.p_tv + per);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (l.mode == MODE_TENSOR) rc = tensor_launch(EPI_TOPK, a, pr.sms, st, g_err, sizeof(g_err));
+  else rc = dispatch_simt<EPI_TOPK>(a, pr.grid, st);
+  if (rc) return rc;
+  k_topk_merge<int><<<l.S, 128, 0, st>>>(a.p_tv, a.p_ti, parts, l.Sp, k, row_offset, out_val,
+                                        reinterpret_cast<long long*>(out_idx));
+  CUDA_TRY(cudaGetLastError());
+  return PSBAX_OK;
+}
+
+int psbax_topk_merge(const float* in_val, const int64_t* in_idx, int32_t lists, int32_t S,
+                     int32_t k, float* out_val, int64_t* out_idx, void* stream) {
+  if (!in_val || !in_idx || !out_val || !out_idx) return fail(PSBAX_E_INVALID, "NULL buffer");
+  if (lists < 1 || S < 1 || k < 1) return fail(PSBAX_E_INVALID, "lists=%d S=%d k=%d must be >= 1", lists, S, k);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_topk_merge<long long><<<S, 128, 0, st>>>(in_val, reinterpret_cast<const long long*>(in_idx), lists,
+                                              S, k, 0LL, out_val, reinterpret_cast<long long*>(out_idx));
+  CUDA_TRY(cudaGetLastError());
+  return PSBAX_OK;
+}
+
+int psbax_subset_select(const float* fx, int64_t ld_fx, const float* etas, int64_t N, int32_t B,
+                        int32_t S, int32_t k, int32_t nonneg, int64_t* out_idx, void* stream) {
+  if (!fx || !etas || !out_idx) return fail(PSBAX_E_INVALID, "NULL buffer");
+  if (N < 1 || B < 1 || S < 1 || k < 1) return fail(PSBAX_E_INVALID, "N, B, S, k must be >= 1");
+  if (k > N) return fail(PSBAX_E_INVALID, "k=%d > N=%lld", k, (long long)N);
+  if (ld_fx < S) return fail(PSBAX_E_INVALID, "ld_fx < S");
+  if (N > 2147483647LL) return fail(PSBAX_E_UNSUPPORTED, "N exceeds 2^31");
+  int sms = 0;
+  int rc = device_sms(&sms);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int T = (S >= 4 * sms) ? 8 : (S >= 2 * sms) ? 4 : 1;
+  const size_t smem = (size_t)T * B * 4 + (size_t)T * k * 4 + (size_t)T * 8 * 8;
+  if (smem > 200 * 1024) return fail(PSBAX_E_UNSUPPORTED, "B=%d too large for shared memory", B);
+  const int grid = (S + T - 1) / T;
+#define LAUNCH_SS(TT)                                                                           \
+  do {                                                                                          \
+    if (smem > 48 * 1024)                                                                       \
+      CUDA_TRY(cudaFuncSetAttribute(k_subset_select<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_subset_select<TT><<<grid, 256, smem, st>>>(fx, ld_fx, etas, N, B, S, k, nonneg,          \
+                                                 reinterpret_cast<long long*>(out_idx));        \
+  } while (0)
+  if (T == 8) LAUNCH_SS(8);
+  else if (T == 4) LAUNCH_SS(4);
+  else LAUNCH_SS(1);
+#undef LAUNCH_SS
+  CUDA_TRY(cudaGetLastError());
+  return PSBAX_OK;
+}
+
+int psbax_eval_grad(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                    const int32_t* sample_idx, float* val, float* grad, void* stream) {
+  Prepared pr;
+  int rc = prepare(paths, pack, X, N, &pr);
+  if (rc) return rc;
+  if (!grad) return fail(PSBAX_E_INVALID, "grad is NULL");
+  const Layout& l = pr.a.lay;
+  const size_t smem = ((size_t)2 * l.dp4 + l.Lp + l.np_ + 8) * sizeof(float);
+  if (smem > 200 * 1024) return fail(PSBAX_E_UNSUPPORTED, "L + n too large for the gradient kernel");
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(k_eval_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_eval_grad<<<(unsigned)N, 128, smem, st>>>(pr.a, sample_idx, val, grad);
+  CUDA_TRY(cudaGetLastError());
+  return PSBAX_OK;
+}
+
+}  // extern "C"

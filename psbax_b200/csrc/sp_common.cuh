@@ -1,0 +1,121 @@
+// Shared definitions for the PS-BAX sample-path kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/psbax_b200.h"
+
+namespace psbax {
+
+constexpr int TM = 128;        // candidate rows per tile
+constexpr int TN = 64;         // sample paths per chunk
+constexpr int TK = 32;         // feature block of the SIMT contraction
+constexpr int OUT_LD = TM + 4; // leading dimension of the staged [TN][TM] value tile
+constexpr int KMAX = 64;       // largest supported k for the fused top-k
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
+
+enum { EPI_VALUES = 0, EPI_LEVELSET = 1, EPI_TOPK = 2 };
+enum { MODE_PERSAMPLE = 0, MODE_SHARED_SIMT = 1, MODE_TENSOR = 2 };
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Device-side operand pack.  All offsets in floats from the pack base.
+//   invls [dp4]                 1/lengthscale, zero padded
+//   ft    [Kp][OS]              shared-basis feature table: rows < Lp are
+//                               (omega[0..dp4) | bias | 0..), rows Lp.. are
+//                               (-Xtrain[0..dp4) | 0..).  Per-sample mode keeps
+//                               only the kernel rows ([np][OS], Lp_ft = 0).
+//   wv    [Kp][Sp]              [W ; V] stacked, K-major (per-sample mode: V rows only)
+//   pb    [S][Lp][OSB]          per-sample table (omega[0..dp4) | bias | w | 0..)
+//   tc    tensor-engine operands (see sp_tensor.cuh)
+struct Layout {
+  int d, L, G, S, n, kernel;
+  int dp4;    // x registers / padded dimension: 2 for d <= 2, else round_up(d, 4)
+  int OS;     // row stride of ft
+  int OSB;    // row stride of pb
+  int Lp;     // L rounded up to 8
+  int np_;    // n rounded up to 8
+  int Lp_ft;  // RFF rows present in ft / wv (Lp in shared modes, 0 in per-sample mode)
+  int Kp;     // rows of ft / wv, multiple of TK
+  int Sp;     // S rounded up to TN
+  int mode;
+  size_t off_invls, off_ft, off_wv, off_pb, off_tc, total_floats;
+};
+
+struct KArgs {
+  Layout lay;
+  const float* pack;
+  const float* X;
+  long long N;
+  long long row_offset;
+  int ntiles;
+  float ystd, c0;  // y = ystd * f + c0, c0 = ystd * mean_const + y_mean
+  // VALUES
+  float* out;
+  long long ld_out;
+  // LEVELSET
+  float tau;
+  uint32_t* mask;
+  long long mask_ld;
+  // per-CTA partial results, [gridDim.x][Sp] (+ [k] for the lists)
+  unsigned int* p_cnt;
+  float* p_max;
+  int* p_arg;
+  int k;
+  float* p_tv;
+  int* p_ti;
+};
+
+// ---------------------------------------------------------------------------------
+// math helpers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Unit-variance stationary kernel profile of the squared scaled distance.
+// kernel id is warp-uniform.  sqrt/ex2 go to the MUFU pipe.
+__device__ __forceinline__ float kernel_profile(float r2, int kernel) {
+  constexpr float LOG2E = 1.4426950408889634f;
+  if (kernel == PSBAX_KERNEL_RBF) return fast_ex2(-0.5f * LOG2E * r2);
+  float r = fast_sqrt(r2);
+  if (kernel == PSBAX_KERNEL_MATERN52) {
+    float s = 2.2360679774997896f * r;
+    return (1.0f + s + 1.6666666666666667f * r2) * fast_ex2(-LOG2E * s);
+  }
+  if (kernel == PSBAX_KERNEL_MATERN32) {
+    float s = 1.7320508075688772f * r;
+    return (1.0f + s) * fast_ex2(-LOG2E * s);
+  }
+  return fast_ex2(-LOG2E * r);
+}
+
+// d kappa / d(r2) * 2  (so that grad_x = dk2 * diff * inv_ls), used by the gradient kernel
+__device__ __forceinline__ float kernel_profile_dr2x2(float r2, int kernel) {
+  if (kernel == PSBAX_KERNEL_RBF) return -__expf(-0.5f * r2);
+  float r = sqrtf(r2);
+  if (kernel == PSBAX_KERNEL_MATERN52) {
+    float s = 2.2360679774997896f * r;
+    return -(5.0f / 3.0f) * (1.0f + s) * __expf(-s);
+  }
+  if (kernel == PSBAX_KERNEL_MATERN32) return -3.0f * __expf(-1.7320508075688772f * r);
+  return r > 0.f ? -__expf(-r) / r : 0.f;
+}
+
+// total order used everywhere a "best" entry is chosen: larger value first, ties
+// towards the smaller index
+template <typename I>
+__device__ __forceinline__ bool better(float v, I i, float v2, I i2) {
+  return v > v2 || (v == v2 && i < i2);
+}
+
+}  // namespace psbax

@@ -1,0 +1,387 @@
+"""GP posterior sample paths on the GPU: drawing their parameters and the fused
+evaluate-and-reduce operations, over the C ABI of ``libpsbax_b200.so``.
+
+Replaces, for the hot path, what ``get_function_samples`` builds from botorch
+(``/root/reference/src/utils.py:185-250``): instead of one opaque callable per
+sample evaluated in Python chunks of 100 candidates
+(``src/algorithms/topk.py:48-49``), a ``SamplePathBatch`` holds the parameters
+of S paths in HBM and evaluates all of them over X* in one kernel launch,
+reduction included.
+
+    f_s(x) = y_mean + y_std * ( mean_const + sum_l W[s,l] cos(omega[g,l].x + b[g,l])
+                                + sum_j V[s,j] kappa(|x/ls - Xtrain_j|) )
+
+There is no CPU implementation here: every evaluation goes through the CUDA
+library and raises ``PsbaxError`` if it is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ENGINE_IDS, KERNEL_IDS, PathsStruct, PsbaxError
+
+F32 = torch.float32
+F64 = torch.float64
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise PsbaxError("no CUDA device: psbax_b200 evaluates sample paths on the GPU only")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+@dataclass
+class LevelSetResult:
+    """Per-sample level-set reduction (``src/algorithms/levelset.py:34-39``)."""
+
+    mask: Optional[torch.Tensor]  # int32 words [S, ceil(N/32)], bit i%32 of word i//32
+    count: torch.Tensor  # int64 [S]
+    maxval: torch.Tensor  # float32 [S]
+    argmax: torch.Tensor  # int64 [S] (row_offset + row)
+    N: int
+
+    def indices(self, s: int) -> torch.Tensor:
+        """Row indices of sample ``s``'s super-level set, or ``[argmax]`` when empty."""
+        if int(self.count[s]) == 0:
+            return self.argmax[s:s + 1].clone()
+        words = self.mask[s]
+        bits = (words.unsqueeze(1) >> torch.arange(32, device=words.device, dtype=torch.int32)) & 1
+        return torch.nonzero(bits.reshape(-1)[: self.N], as_tuple=False).reshape(-1)
+
+
+class SamplePathBatch:
+    """S sample paths resident on one GPU."""
+
+    def __init__(self, omega, bias, W, kernel: str = "matern52", Xtrain=None, inv_ls=None, V=None,
+                 mean_const: float = 0.0, y_mean: float = 0.0, y_std: float = 1.0,
+                 device: Optional[torch.device] = None, engine: str = "auto"):
+        self.device = torch.device(device) if device is not None else default_device()
+        if self.device.type != "cuda":
+            raise PsbaxError("SamplePathBatch needs a CUDA device")
+        self.lib = _lib.load()
+
+        def dev(t):
+            return None if t is None else torch.as_tensor(t).to(self.device, F32).contiguous()
+
+        self.omega, self.bias, self.W = dev(omega), dev(bias), dev(W)
+        self.Xtrain, self.inv_ls, self.V = dev(Xtrain), dev(inv_ls), dev(V)
+        if self.omega.dim() != 3 or self.W.dim() != 2:
+            raise PsbaxError("omega must be [G, L, d] and W [S, L]")
+        self.G, self.L, self.d = self.omega.shape
+        self.S = self.W.shape[0]
+        self.n = 0 if self.V is None else self.V.shape[1]
+        if self.n == 0:
+            self.Xtrain = self.inv_ls = self.V = None
+        self.kernel = kernel
+        self.engine = engine
+        self.mean_const, self.y_mean, self.y_std = float(mean_const), float(y_mean), float(y_std)
+        if kernel not in KERNEL_IDS:
+            raise NotImplementedError(f"kernel {kernel!r}")  # botorch RandomFourierFeatures raises too
+        if tuple(self.bias.shape) != (self.G, self.L) or self.W.shape[1] != self.L:
+            raise PsbaxError("bias must be [G, L] and W [S, L]")
+        if self.n and (tuple(self.Xtrain.shape) != (self.n, self.d) or self.V.shape[0] != self.S
+                       or self.inv_ls.numel() != self.d):
+            raise PsbaxError("Xtrain must be [n, d], V [S, n], inv_ls [d]")
+        self._struct = PathsStruct(
+            d=self.d, L=self.L, G=self.G, S=self.S, n=self.n, kernel=KERNEL_IDS[kernel],
+            engine=ENGINE_IDS[engine], reserved=0,
+            omega=_ptr(self.omega) if self.L else None, bias=_ptr(self.bias) if self.L else None,
+            W=_ptr(self.W) if self.L else None, Xtrain=_ptr(self.Xtrain), inv_ls=_ptr(self.inv_ls),
+            V=_ptr(self.V), mean_const=self.mean_const, y_mean=self.y_mean, y_std=self.y_std,
+            reserved_f=0.0)
+        self._pack = None
+        self._ws = None
+        self._build_pack()
+
+    # -- plumbing --------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _build_pack(self) -> None:
+        nbytes = C.c_size_t(0)
+        _lib.check(self.lib.psbax_pack_bytes(C.byref(self._struct), C.byref(nbytes)), "psbax_pack_bytes")
+        with torch.cuda.device(self.device):
+            self._pack = torch.empty((nbytes.value + 3) // 4, dtype=F32, device=self.device)
+            _lib.check(self.lib.psbax_pack(C.byref(self._struct), self._pack.data_ptr(),
+                                           self._pack.numel() * 4, self._stream()), "psbax_pack")
+
+    def _workspace(self, N: int, k: int) -> torch.Tensor:
+        nbytes = C.c_size_t(0)
+        _lib.check(self.lib.psbax_workspace_bytes(C.byref(self._struct), N, k, C.byref(nbytes)),
+                   "psbax_workspace_bytes")
+        if self._ws is None or self._ws.numel() < nbytes.value:
+            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _x(self, X) -> torch.Tensor:
+        X = torch.as_tensor(X)
+        if X.shape[-1] != self.d:
+            raise PsbaxError(f"X has last dim {X.shape[-1]}, paths expect d={self.d}")
+        X = X.reshape(-1, self.d)
+        if X.device != self.device or X.dtype != F32 or not X.is_contiguous():
+            X = X.to(self.device, F32).contiguous()
+        return X
+
+    # -- operations ------------------------------------------------------------------
+    def values(self, X) -> torch.Tensor:
+        """f_s(X[i]) for every sample: [N, S] float32 on the GPU."""
+        X = self._x(X)
+        N = X.shape[0]
+        with torch.cuda.device(self.device):
+            out = torch.empty(N, self.S, dtype=F32, device=self.device)
+            _lib.check(self.lib.psbax_eval_values(C.byref(self._struct), self._pack.data_ptr(),
+                                                  X.data_ptr(), N, out.data_ptr(), self.S,
+                                                  self._stream()), "psbax_eval_values")
+        return out
+
+    def levelset(self, X, threshold: float, want_mask: bool = True, row_offset: int = 0) -> LevelSetResult:
+        """Fused evaluation + ``fx > threshold`` for all S paths."""
+        X = self._x(X)
+        N = X.shape[0]
+        with torch.cuda.device(self.device):
+            words = (N + 31) // 32
+            mask = torch.empty(self.S, words, dtype=torch.int32, device=self.device) if want_mask else None
+            count = torch.empty(self.S, dtype=torch.int64, device=self.device)
+            maxval = torch.empty(self.S, dtype=F32, device=self.device)
+            argmax = torch.empty(self.S, dtype=torch.int64, device=self.device)
+            ws = self._workspace(N, 0)
+            _lib.check(self.lib.psbax_eval_levelset(
+                C.byref(self._struct), self._pack.data_ptr(), X.data_ptr(), N, row_offset,
+                float(threshold), _ptr(mask), words, count.data_ptr(), maxval.data_ptr(),
+                argmax.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()), "psbax_eval_levelset")
+        return LevelSetResult(mask, count, maxval, argmax, N)
+
+    def argmax(self, X, row_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Per-sample max and arg max over the candidates (ES-population scoring)."""
+        r = self.levelset(X, float("inf"), want_mask=False, row_offset=row_offset)
+        return r.maxval, r.argmax
+
+    def topk(self, X, k: int, row_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Fused evaluation + per-sample top-k: (values [S, k], indices [S, k])."""
+        X = self._x(X)
+        N = X.shape[0]
+        with torch.cuda.device(self.device):
+            val = torch.empty(self.S, k, dtype=F32, device=self.device)
+            idx = torch.empty(self.S, k, dtype=torch.int64, device=self.device)
+            ws = self._workspace(N, k)
+            _lib.check(self.lib.psbax_eval_topk(
+                C.byref(self._struct), self._pack.data_ptr(), X.data_ptr(), N, row_offset, k,
+                val.data_ptr(), idx.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()),
+                "psbax_eval_topk")
+        return val, idx
+
+    def grad(self, X, sample_idx=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(f_{s_i}(X[i]), d f_{s_i} / dx (X[i])) for (point, sample) pairs."""
+        X = self._x(X)
+        N = X.shape[0]
+        with torch.cuda.device(self.device):
+            si = None
+            if sample_idx is not None:
+                si = torch.as_tensor(sample_idx).to(self.device, torch.int32).contiguous().reshape(-1)
+                if si.numel() != N:
+                    raise PsbaxError("sample_idx must have one entry per row of X")
+            val = torch.empty(N, dtype=F32, device=self.device)
+            g = torch.empty(N, self.d, dtype=F32, device=self.device)
+            _lib.check(self.lib.psbax_eval_grad(C.byref(self._struct), self._pack.data_ptr(),
+                                                X.data_ptr(), N, _ptr(si), val.data_ptr(),
+                                                g.data_ptr(), self._stream()), "psbax_eval_grad")
+        return val, g
+
+    def subset_select(self, X, etas, k: int, nonneg: bool = False) -> torch.Tensor:
+        """DiscoBAX greedy subset per sample (``src/algorithms/discobax.py:37-56``): [S, k] indices."""
+        fx = self.values(X)
+        N = fx.shape[0]
+        etas = torch.as_tensor(etas).to(self.device, F32).contiguous()
+        if etas.dim() != 2 or etas.shape[1] != N:
+            raise PsbaxError("etas must be [B, N]")
+        with torch.cuda.device(self.device):
+            out = torch.empty(self.S, k, dtype=torch.int64, device=self.device)
+            _lib.check(self.lib.psbax_subset_select(fx.data_ptr(), self.S, etas.data_ptr(), N,
+                                                    etas.shape[0], self.S, k, int(bool(nonneg)),
+                                                    out.data_ptr(), self._stream()),
+                       "psbax_subset_select")
+        return out
+
+    def path(self, s: int) -> "SamplePath":
+        return SamplePath(self, s)
+
+    def __len__(self) -> int:
+        return self.S
+
+    def __iter__(self):
+        return (self.path(s) for s in range(self.S))
+
+
+class _PathValue(torch.autograd.Function):
+    """f_s(X) with the CUDA gradient kernel as backward (LBFGSB needs d f / d x,
+    ``src/algorithms/lbfgsb.py:29-39``)."""
+
+    @staticmethod
+    def forward(ctx, X, path):
+        val, g = path.batch.grad(X.detach().reshape(-1, path.batch.d),
+                                 torch.full((X.numel() // path.batch.d,), path.s, dtype=torch.int32))
+        ctx.save_for_backward(g.to(X.device, X.dtype).reshape(X.shape))
+        return val.to(X.device, X.dtype)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (g,) = ctx.saved_tensors
+        return g * gout.reshape(-1, *([1] * (g.dim() - 1))), None
+
+
+class SamplePath:
+    """One sample path with the calling convention of the object
+    ``get_function_samples`` returns for a ``SingleTaskGP``
+    (``PosteriorMean(sample)``, ``src/utils.py:229``): X [b, 1, d] -> [b];
+    X [b, d] -> [b].  Output follows X's dtype/device."""
+
+    def __init__(self, batch: SamplePathBatch, s: int):
+        if not 0 <= s < batch.S:
+            raise IndexError(s)
+        self.batch, self.s = batch, s
+        self._single = None
+
+    def _one(self) -> SamplePathBatch:
+        # a one-sample view so that repeated legacy calls do not evaluate all S paths
+        if self._single is None:
+            b, s = self.batch, self.s
+            if b.S == 1:
+                self._single = b
+            else:
+                g = 0 if b.G == 1 else s
+                self._single = SamplePathBatch(
+                    b.omega[g:g + 1], b.bias[g:g + 1], b.W[s:s + 1], b.kernel, b.Xtrain, b.inv_ls,
+                    None if b.V is None else b.V[s:s + 1], b.mean_const, b.y_mean, b.y_std,
+                    b.device, "simt")
+        return self._single
+
+    def __call__(self, X) -> torch.Tensor:
+        X = torch.as_tensor(X)
+        d = self.batch.d
+        if X.dim() == 3 and X.shape[1] != 1:
+            raise PsbaxError("expected X of shape [b, 1, d] (q = 1)")
+        if X.requires_grad:
+            flat = X.reshape(-1, d)
+            return _PathValue.apply(flat, self)
+        out = self._one().values(X.reshape(-1, d))[:, 0]
+        dtype = X.dtype if X.dtype.is_floating_point else F64
+        return out.to(device=X.device, dtype=dtype)
+
+
+# ------------------------------------------------------------------------------------
+# Parameter draws (torch; the n x n / L x L factorisations stay in cuSOLVER via torch)
+# ------------------------------------------------------------------------------------
+def _basis(d, L, kernel, G, gen, dev):
+    """botorch ``RandomFourierFeatures.__init__``: randn(d, L),
+    Matern columns scaled by rsqrt(Gamma(nu, nu)), bias = 2 pi rand(L); G independent bases."""
+    w = torch.randn(G, d, L, dtype=F64, device=dev, generator=gen)
+    if kernel != "rbf":
+        nu = {"matern12": 0.5, "matern32": 1.5, "matern52": 2.5}[kernel]
+        g = torch._standard_gamma(torch.full((G, 1, L), nu, dtype=F64, device=dev), generator=gen) / nu
+        w = torch.rsqrt(g) * w
+    b = 2.0 * math.pi * torch.rand(G, L, dtype=F64, device=dev, generator=gen)
+    return w, b
+
+
+def _model_state(model, dev):
+    X = model.train_inputs[0].to(dev, F64)
+    y = model.train_targets.to(dev, F64)
+    ls = model.lengthscale_vector().to(dev, F64)
+    alpha = float(model.covar_module.outputscale)
+    noise = float(model.likelihood.noise.mean())
+    mu = float(model.mean_module.constant)
+    y_mean, y_std = model.y_mean_std()
+    return X, y, ls, alpha, noise, mu, y_mean, y_std
+
+
+def matheron_params(model, S: int, L: int = 1000, generator: Optional[torch.Generator] = None,
+                    device=None) -> dict:
+    """Parameters of S pathwise (Matheron) posterior samples, the north-star form: shared
+    RFF basis, prior weights w_s ~ N(0, I), exact-kernel update
+    v_s = (K + sigma^2 I)^-1 (y - mu - Phi w_s - eps_s).  One n x n Cholesky for all S.
+    Pure torch (float64) on ``device``; returns the keyword arguments of ``SamplePathBatch``."""
+    dev = torch.device(device) if device is not None else default_device()
+    X, y, ls, alpha, noise, mu, y_mean, y_std = _model_state(model, dev)
+    n, d = X.shape
+    kernel = model.kernel
+    wts, b = _basis(d, L, kernel, 1, generator, dev)
+    omega = (wts[0] / ls[:, None]).T.contiguous()  # [L, d]
+    scale = math.sqrt(2.0 * alpha / L)
+    Phi = scale * torch.cos(X @ omega.T + b[0])  # [n, L]
+    w = torch.randn(S, L, dtype=F64, device=dev, generator=generator)
+    eps = math.sqrt(noise) * torch.randn(S, n, dtype=F64, device=dev, generator=generator)
+    Lk = model.train_cholesky().to(dev)
+    resid = y[None, :] - mu - w @ Phi.T - eps
+    v = torch.cholesky_solve(resid.T, Lk).T  # [S, n]
+    return dict(omega=omega[None], bias=b, W=scale * w, kernel=kernel, Xtrain=X / ls,
+                inv_ls=1.0 / ls, V=alpha * v, mean_const=mu, y_mean=y_mean, y_std=y_std)
+
+
+def reference_params(model, S: int, L: int = 1000, generator: Optional[torch.Generator] = None,
+                     device=None) -> dict:
+    """Parameters of S samples drawn with the reference's scheme (``src/utils.py:222-229`` ->
+    botorch ``get_gp_samples``): a fresh basis per sample and w_s ~ N(m, sigma^2 A^-1),
+    A = Phi^T Phi + sigma^2 I; no exact-kernel term; the GP constant mean is not used.
+    Batched over the samples."""
+    dev = torch.device(device) if device is not None else default_device()
+    X, y, ls, alpha, noise, _mu, y_mean, y_std = _model_state(model, dev)
+    n, d = X.shape
+    kernel = model.kernel
+    wts, b = _basis(d, L, kernel, S, generator, dev)
+    omega = (wts / ls[None, :, None]).transpose(1, 2).contiguous()  # [S, L, d]
+    scale = math.sqrt(2.0 * alpha / L)
+    Ws = []
+    eye = torch.eye(L, dtype=F64, device=dev)
+    for s0 in range(0, S, 16):  # chunks bound the S x L x L workspace
+        om = omega[s0:s0 + 16]
+        Phi = scale * torch.cos(torch.einsum("nd,sld->snl", X, om) + b[s0:s0 + 16, None, :])
+        A = Phi.transpose(1, 2) @ Phi + noise * eye
+        LA = torch.linalg.cholesky(A)
+        rhs = Phi.transpose(1, 2) @ y[None, :, None].expand(om.shape[0], n, 1)
+        m = torch.cholesky_solve(rhs, LA)[..., 0]
+        # w = m + sqrt(noise) * LA^-T z has covariance noise * A^-1
+        z = torch.randn(om.shape[0], L, 1, dtype=F64, device=dev, generator=generator)
+        u = torch.linalg.solve_triangular(LA.transpose(1, 2), z, upper=True)[..., 0]
+        Ws.append(m + math.sqrt(noise) * u)
+    return dict(omega=omega, bias=b, W=scale * torch.cat(Ws), kernel=kernel, Xtrain=None,
+                inv_ls=None, V=None, mean_const=0.0, y_mean=y_mean, y_std=y_std)
+
+
+def posterior_mean_params(model, device=None) -> dict:
+    """``PosteriorMean(model)`` as a one-sample path with L = 0:
+    mu(x) = mean_const + k(x, X) (K + sigma^2 I)^-1 (y - mean_const)
+    (what ``src/performance_metrics.py:117-122`` feeds the algorithms)."""
+    dev = torch.device(device) if device is not None else default_device()
+    X, y, ls, alpha, noise, mu, y_mean, y_std = _model_state(model, dev)
+    d = X.shape[1]
+    Lk = model.train_cholesky().to(dev)
+    a = torch.cholesky_solve((y - mu)[:, None], Lk)[:, 0]
+    return dict(omega=torch.zeros(1, 0, d), bias=torch.zeros(1, 0), W=torch.zeros(1, 0),
+                kernel=model.kernel, Xtrain=X / ls, inv_ls=1.0 / ls, V=(alpha * a)[None],
+                mean_const=mu, y_mean=y_mean, y_std=y_std)
+
+
+def draw_matheron_paths(model, S: int, L: int = 1000, generator=None, device=None,
+                        engine: str = "auto") -> SamplePathBatch:
+    dev = torch.device(device) if device is not None else default_device()
+    return SamplePathBatch(**matheron_params(model, S, L, generator, dev), device=dev, engine=engine)
+
+
+def draw_reference_paths(model, S: int, L: int = 1000, generator=None, device=None) -> SamplePathBatch:
+    dev = torch.device(device) if device is not None else default_device()
+    return SamplePathBatch(**reference_params(model, S, L, generator, dev), device=dev, engine="simt")
+
+
+def posterior_mean_path(model, device=None) -> SamplePathBatch:
+    dev = torch.device(device) if device is not None else default_device()
+    return SamplePathBatch(**posterior_mean_params(model, dev), device=dev, engine="simt")
