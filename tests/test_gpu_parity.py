@@ -1,0 +1,241 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the float64 oracle on the same
+seeded float32-representable inputs.
+
+Tolerance (BASELINE.json north_star: "sample values within 1e-4 relative in fp32, index sets
+identical wherever the score gap exceeds that tolerance"): per sample
+    tol_s = 1e-4 * y_std * max(1, ||W_s||_2 + ||V_s||_2)          (oracle.path_scale)
+i.e. relative to the natural forward-error scale of the two dot products.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, candidates, make_gp, random_params, to_batch, unpack_mask
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4
+
+# (S, L, d, n, G, kernel, N)
+CASES = [
+    (64, 1000, 2, 64, 1, "matern52", 4096),     # C2 shape (level-set grid)
+    (64, 1000, 2, 64, 1, "rbf", 1000),          # ragged N
+    (32, 256, 10, 122, 1, "matern52", 3001),    # C5 shape (Ackley-10D), generic-d path
+    (256, 200, 5, 128, 1, "matern32", 1500),    # several sample chunks
+    (16, 128, 3, 0, 1, "matern52", 777),        # no kernel term
+    (20, 96, 4, 17, 1, "matern12", 513),        # S not a multiple of anything
+    (8, 1000, 3, 0, 8, "matern52", 2048),       # reference form: one basis per sample
+    (64, 120, 2, 0, 64, "rbf", 300),            # reference form, full chunk
+    (5, 64, 6, 9, 5, "matern52", 129),          # per-sample basis + kernel term, d=6
+    (1, 1000, 3, 0, 1, "matern52", 100),        # C1 demo shape: one path, 100 points
+    (1, 0, 3, 38, 1, "matern52", 100),          # posterior mean: L = 0
+    (3, 40, 80, 12, 1, "rbf", 260),             # d = 80 (GB1 one-hot width), small-S route
+    (24, 72, 80, 16, 1, "matern52", 200),       # d = 80 on the shared-basis route
+    (2, 8, 1, 3, 2, "matern32", 33),            # tiny everything
+]
+
+
+def _tol(p):
+    return (REL * O.path_scale(p)).numpy()
+
+
+@pytest.fixture(scope="module", params=CASES, ids=lambda c: "S%d_L%d_d%d_n%d_G%d_%s_N%d" % c)
+def case(request):
+    S, L, d, n, G, kernel, N = request.param
+    p = random_params(S, L, d, n, G=G, kernel=kernel, seed=S + L + d)
+    X = candidates(N, d)
+    ref = O.eval_paths(p, X.double()).numpy()  # [N, S] float64
+    return p, X, ref, to_batch(p)
+
+
+def test_values(case):
+    p, X, ref, batch = case
+    out = batch.values(X.cuda()).double().cpu().numpy()
+    assert out.shape == ref.shape
+    err = np.abs(out - ref).max(axis=0)
+    assert (err <= _tol(p)).all(), (err / _tol(p)).max()
+
+
+def test_levelset(case):
+    p, X, ref, batch = case
+    tol = _tol(p)
+    for tau in (float(np.quantile(ref, 0.55)), float(ref.max() + 10.0), float(ref.min() - 10.0)):
+        res = batch.levelset(X.cuda(), tau)
+        mask = unpack_mask(res.mask, X.shape[0])  # [S, N]
+        want = (ref > tau).T
+        decided = (np.abs(ref - tau) > tol[None, :]).T
+        assert (mask[decided] == want[decided]).all()
+        count = res.count.cpu().numpy()
+        assert (count == mask.sum(1)).all()
+        lo = (want & decided).sum(1)
+        hi = lo + (~decided).sum(1)
+        assert ((count >= lo) & (count <= hi)).all()
+        # arg max (the empty-set fallback of levelset.py:35-37)
+        am = res.argmax.cpu().numpy()
+        mv = res.maxval.double().cpu().numpy()
+        best = ref.max(axis=0)
+        assert (np.abs(mv - best) <= tol).all()
+        assert (np.abs(ref[am, np.arange(ref.shape[1])] - best) <= 2 * tol).all()
+        for s in range(ref.shape[1]):
+            idx = res.indices(s).cpu().numpy()
+            if count[s] == 0:
+                assert idx.tolist() == [am[s]]
+            else:
+                assert (idx == np.nonzero(mask[s])[0]).all()
+
+
+def test_argmax_only(case):
+    p, X, ref, batch = case
+    mv, am = batch.argmax(X.cuda(), row_offset=1000)
+    tol = _tol(p)
+    best = ref.max(axis=0)
+    assert (np.abs(mv.double().cpu().numpy() - best) <= tol).all()
+    am = am.cpu().numpy() - 1000
+    assert (np.abs(ref[am, np.arange(ref.shape[1])] - best) <= 2 * tol).all()
+
+
+@pytest.mark.parametrize("k", [1, 4, 10, 64])
+def test_topk(case, k):
+    p, X, ref, batch = case
+    N, S = ref.shape
+    if k > N:
+        pytest.skip("k > N")
+    tol = _tol(p)
+    val, idx = batch.topk(X.cuda(), k)
+    val, idx = val.double().cpu().numpy(), idx.cpu().numpy()
+    for s in range(S):
+        oidx, oval = O.topk_reduce(torch.from_numpy(ref[:, s]), k)
+        oidx, oval = oidx.numpy(), oval.numpy()
+        assert len(set(idx[s].tolist())) == k
+        # values agree position by position, and are the oracle's values at the chosen rows
+        assert (np.abs(val[s] - oval) <= tol[s]).all()
+        assert (np.abs(ref[idx[s], s] - val[s]) <= tol[s]).all()
+        assert (np.diff(val[s]) <= 0).all()
+        # index sets identical wherever the gap to the first excluded value exceeds tolerance
+        order = np.sort(ref[:, s])[::-1]
+        kth, nxt = order[k - 1], (order[k] if k < N else -np.inf)
+        if kth - nxt > 2 * tol[s]:
+            assert set(idx[s].tolist()) == set(oidx.tolist())
+        sure = oidx[oval - nxt > 2 * tol[s]]
+        assert set(sure.tolist()) <= set(idx[s].tolist())
+
+
+def test_ties_break_towards_smaller_index():
+    p = random_params(16, 64, 2, 8, seed=3)
+    base = candidates(50, 2)
+    X = torch.cat([base, base, base])  # every value appears three times, bit-identically
+    batch = to_batch(p)
+    val, idx = batch.topk(X.cuda(), 6)
+    idx, val = idx.cpu().numpy(), val.cpu().numpy()
+    for s in range(16):
+        assert (val[s, 0] == val[s, 1]) and (val[s, 1] == val[s, 2])
+        assert idx[s, 0] + 50 == idx[s, 1] and idx[s, 1] + 50 == idx[s, 2] and idx[s, 0] < 50
+        assert idx[s, 3] + 50 == idx[s, 4] and idx[s, 4] + 50 == idx[s, 5]
+    _, am = batch.argmax(X.cuda())
+    assert (am.cpu().numpy() == idx[:, 0]).all()
+
+
+def test_row_offset_and_sharded_merge_equal_whole():
+    """Shards of the candidate set + psbax_topk_merge == one launch over the whole set, bit for bit."""
+    import ctypes as C
+
+    from psbax_b200 import _lib
+
+    p = random_params(64, 200, 3, 20, seed=9)
+    X = candidates(5000, 3).cuda()
+    batch = to_batch(p)
+    k = 10
+    val, idx = batch.topk(X, k)
+    cuts = [0, 1300, 1301, 4000, 5000]
+    vs, is_ = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        kk = min(k, b - a)
+        v, i = batch.topk(X[a:b], kk, row_offset=a)
+        pad_v = torch.full((64, k), -float("inf"), device="cuda")
+        pad_i = torch.full((64, k), -1, dtype=torch.int64, device="cuda")
+        pad_v[:, :kk], pad_i[:, :kk] = v, i
+        vs.append(pad_v)
+        is_.append(pad_i)
+    lv, li = torch.stack(vs).contiguous(), torch.stack(is_).contiguous()
+    ov = torch.empty(64, k, device="cuda")
+    oi = torch.empty(64, k, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.load().psbax_topk_merge(lv.data_ptr(), li.data_ptr(), len(vs), 64, k, ov.data_ptr(),
+                                            oi.data_ptr(), torch.cuda.current_stream().cuda_stream), "merge")
+    assert torch.equal(oi, idx) and torch.equal(ov, val)
+    # level set: shard masks concatenate to the whole mask, counts add up
+    tau = 0.0
+    whole = batch.levelset(X, tau)
+    a = batch.levelset(X[:2048], tau)
+    b = batch.levelset(X[2048:], tau, row_offset=2048)
+    assert torch.equal(a.count + b.count, whole.count)
+    assert torch.equal(torch.cat([a.mask, b.mask], 1), whole.mask)
+    gm = torch.where(a.maxval >= b.maxval, a.argmax, b.argmax)
+    assert torch.equal(gm, whole.argmax)
+
+
+def test_grad_matches_oracle():
+    for (S, L, d, n, G, kernel) in [(4, 300, 3, 10, 1, "matern52"), (3, 100, 10, 20, 3, "rbf"),
+                                    (20, 64, 2, 8, 1, "matern32")]:
+        p = random_params(S, L, d, n, G=G, kernel=kernel, seed=4)
+        batch = to_batch(p)
+        X = candidates(40, d)
+        sidx = torch.arange(40) % S
+        val, g = batch.grad(X.cuda(), sidx)
+        ref = O.eval_paths(p, X.double())
+        for s in range(S):
+            rows = (sidx == s).nonzero().reshape(-1)
+            og = O.eval_path_grad(p, X[rows].double(), s).numpy()
+            gnorm = max(1.0, float(np.abs(og).max()))
+            assert np.abs(g[rows].double().cpu().numpy() - og).max() <= 2e-4 * gnorm * float(O.path_scale(p)[s])
+            assert np.abs(val[rows].double().cpu().numpy() - ref[rows, s].numpy()).max() <= _tol(p)[s]
+
+
+def test_subset_select_matches_oracle():
+    for (S, N, B, k, nonneg) in [(3, 300, 20, 5, False), (40, 500, 16, 10, True), (700, 120, 8, 4, False)]:
+        p = random_params(S, 64, 5, 12, seed=S)
+        X = candidates(N, 5)
+        g = torch.Generator().manual_seed(2)
+        etas = 0.7 * torch.randn(B, N, generator=g)
+        batch = to_batch(p)
+        idx = batch.subset_select(X.cuda(), etas, k, nonneg).cpu().numpy()
+        fx = batch.values(X.cuda()).double().cpu().numpy()  # same values the GPU greedy saw
+        for s in range(0, S, max(1, S // 7)):
+            oidx, values = O.subset_select_reduce(fx[:, s], etas.double().numpy(), k, nonneg)
+            if idx[s].tolist() == oidx:
+                continue
+            # float32 vs float64 means may swap near-ties: the greedy objective must still agree
+            def score(sel):
+                return np.max(values[:, sel], axis=1).mean()
+            assert abs(score(idx[s].tolist()) - score(oidx)) <= 1e-5 * max(1.0, abs(score(oidx)))
+
+
+def test_single_path_callable_protocol():
+    p = random_params(3, 128, 3, 6, seed=5)
+    batch = to_batch(p)
+    X = candidates(250, 3).double()
+    ref = O.eval_paths(p, X).numpy()
+    f = batch.path(1)
+    y = torch.cat([f(c) for c in X.unsqueeze(1).split(100)])  # eval_in_batch, topk.py:48-49
+    assert y.dtype == torch.float64 and y.device.type == "cpu" and y.shape == (250,)
+    assert np.abs(y.numpy() - ref[:, 1]).max() <= _tol(p)[1]
+    assert f(X[:7]).shape == (7,)
+    Xg = X[:5].clone().requires_grad_(True)
+    f(Xg).sum().backward()
+    og = O.eval_path_grad(p, X[:5], 1).numpy()
+    assert np.abs(Xg.grad.numpy() - og).max() <= 2e-4 * max(1.0, np.abs(og).max()) * float(O.path_scale(p)[1])
+
+
+def test_errors_are_reported():
+    from psbax_b200 import PsbaxError
+
+    p = random_params(4, 32, 2, 0, seed=1)
+    batch = to_batch(p)
+    X = candidates(10, 2).cuda()
+    with pytest.raises(PsbaxError):
+        batch.topk(X, 11)  # k > N, torch.topk raises too
+    with pytest.raises(PsbaxError):
+        batch.topk(X, 65)
+    with pytest.raises(PsbaxError):
+        batch.values(candidates(10, 3).cuda())

@@ -1,0 +1,195 @@
+"""CPU tests of the host-side mirror of the reference interface: algorithm classes on foreign
+callables (checked against the golden vectors the reference's own classes produced), the GP
+stand-in, the entropy pick, parameter draws (run on the CPU in float64 and evaluated by the
+oracle), and the missing-library failure mode."""
+import math
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, O, make_gp
+
+from psbax_b200.acquisition_functions.entropy import EntropyAcquisitionFunction, optimize_acqf_discrete
+from psbax_b200.algorithms import LevelSetEstimator, SubsetSelect, TopK
+from psbax_b200.models import SingleTaskGP
+from psbax_b200.sample_paths import matheron_params, posterior_mean_params, reference_params
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN, allow_pickle=False)
+
+
+class _PM:
+    """A foreign callable with botorch's PosteriorMean convention: X [b, 1, d] -> [b]."""
+    expects_q_dim = True
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self, X):
+        if X.dim() == 2:
+            return self.fn(X)[0]
+        assert X.dim() == 3 and X.shape[1] == 1
+        return self.fn(X.squeeze(1))
+
+
+def _fn(g, pre):
+    A, c, w = (torch.from_numpy(g[pre + k]) for k in ("A", "c", "w"))
+    return lambda X: torch.cos(torch.as_tensor(X, dtype=torch.float64) @ A + c) @ w
+
+
+def test_topk_class_matches_reference_golden(golden):
+    for i in range(int(golden["n_topk"])):
+        pre = f"topk{i}_"
+        f = _fn(golden, pre)
+        algo = TopK({"x_path": golden[pre + "x"].copy(), "k": int(golden[pre + "k"])})
+        exe_path, out = algo.run_algorithm_on_f(_PM(f) if bool(golden[pre + "as_pm"]) else f)
+        assert exe_path.idx == golden[pre + "idx"].tolist()
+        np.testing.assert_array_equal(out.numpy(), golden[pre + "out_x"])
+        np.testing.assert_allclose(exe_path.y.numpy(), golden[pre + "out_y"], atol=1e-12)
+        assert algo.execute(f).shape == out.shape
+
+
+def test_levelset_class_matches_reference_golden(golden):
+    for i in range(int(golden["n_ls"])):
+        pre = f"ls{i}_"
+        f = _fn(golden, pre)
+        algo = LevelSetEstimator({"name": "SimpleLevelSet", "threshold": float(golden[pre + "thr"]),
+                                  "x_set": golden[pre + "x"].copy()})
+        exe_path, out = algo.run_algorithm_on_f(_PM(f) if bool(golden[pre + "as_pm"]) else f)
+        assert [int(j) for j in exe_path.idx] == golden[pre + "idx"].tolist()
+        np.testing.assert_array_equal(out, golden[pre + "out_x"])
+        np.testing.assert_allclose(exe_path.y, golden[pre + "out_y"], atol=1e-12)
+
+
+class _Obj:
+    def __init__(self, x, etas, nonneg):
+        self._x, self.etas, self.nonneg = torch.as_tensor(x), np.asarray(etas), nonneg
+        self.noise_type = "additive"
+        self.df = types.SimpleNamespace(index=[f"g{i}" for i in range(self._x.shape[0])])
+
+    def get_x(self, idx=None):
+        return self._x
+
+    def get_noisy_f_lst(self, fx):
+        v = fx.squeeze() + self.etas
+        return np.maximum(0, v) if self.nonneg else v
+
+
+def test_subset_select_class_matches_reference_golden(golden):
+    for i in range(int(golden["n_ss"])):
+        pre = f"ss{i}_"
+        f = _fn(golden, pre)
+        x = golden[pre + "x"]
+        algo = SubsetSelect({"k": int(golden[pre + "k"])})
+        algo.set_obj_func(_Obj(x, golden[pre + "etas"], bool(golden[pre + "nonneg"])))
+        arg = f(x).numpy() if bool(golden[pre + "as_array"]) else f
+        exe_path, labels = algo.run_algorithm_on_f(arg)
+        assert exe_path.idxes == golden[pre + "idxes"].tolist()
+        assert list(labels) == golden[pre + "labels"].tolist()
+        np.testing.assert_allclose(exe_path.values, golden[pre + "values"], atol=1e-12)
+        assert algo.get_values_and_selected_indices()[1] == exe_path.idxes
+
+
+def test_algorithm_params_and_copy():
+    x = np.random.default_rng(0).uniform(size=(10, 2))
+    algo = TopK({"x_path": x, "k": 3})
+    assert algo.params.name == "TopK" and isinstance(algo.params.x_path, torch.Tensor)
+    cp = algo.get_copy()
+    assert cp is not algo and torch.equal(cp.params.x_path, algo.params.x_path)
+    ls = LevelSetEstimator({"x_set": x, "threshold": 0.5})
+    assert ls.params.name == "SimpleLevelSet" and isinstance(ls.params.x_set, np.ndarray)
+    with pytest.raises(AttributeError):
+        TopK(None)  # params must be a dict, as in the reference
+
+
+def _model_from(gp):
+    return SingleTaskGP(gp.train_X, gp.train_Y, kernel=gp.kernel, lengthscale=gp.lengthscale,
+                        outputscale=gp.outputscale, noise=gp.noise, mean_const=gp.mean_const)
+
+
+def test_gp_standin_posterior_matches_oracle():
+    gp = make_gp(14, 3, noise=1e-2)
+    m = _model_from(gp)
+    np.testing.assert_allclose(m.train_targets.numpy(), gp.train_targets.numpy(), atol=1e-12)
+    X = torch.rand(6, 3, dtype=torch.float64)
+    post = m.posterior(X)
+    mean, cov = O.gp_posterior(gp, X)
+    np.testing.assert_allclose(post.mean[:, 0].numpy(), mean.numpy(), atol=1e-9)
+    np.testing.assert_allclose(post.covariance_matrix.numpy(), cov.numpy(), atol=1e-9)
+    assert post.variance.shape == (6, 1)
+
+
+def test_entropy_pick_matches_oracle():
+    gp = make_gp(10, 2, noise=1e-2)
+    m = _model_from(gp)
+    choices = torch.rand(23, 2, dtype=torch.float64)
+    acq = EntropyAcquisitionFunction(m)
+    np.testing.assert_allclose(acq(choices[:5].unsqueeze(1)).numpy(),
+                               O.entropy_acqf(gp, choices[:5].unsqueeze(1)).numpy(), atol=1e-9)
+    x_next, _ = optimize_acqf_discrete(acq, 3, choices, max_batch_size=7)
+    ref, _ = O.optimize_acqf_discrete(gp, choices, 3)
+    np.testing.assert_allclose(x_next.numpy(), ref.numpy())
+    assert acq.X_pending is None
+
+
+def _as_oracle(params):
+    t = lambda v: None if v is None else v.double().cpu()  # noqa: E731
+    return O.PathParams(omega=t(params["omega"]), bias=t(params["bias"]), W=t(params["W"]),
+                        kernel=params["kernel"], Xtrain=t(params["Xtrain"]), inv_ls=t(params["inv_ls"]),
+                        V=t(params["V"]), mean_const=params["mean_const"], y_mean=params["y_mean"],
+                        y_std=params["y_std"])
+
+
+@pytest.mark.parametrize("draw", [matheron_params, reference_params])
+def test_param_draws_interpolate_and_average_to_posterior_mean(draw):
+    gp = make_gp(9, 2, noise=1e-6, ls=torch.tensor([0.4, 0.5]))
+    m = _model_from(gp)
+    gen = torch.Generator().manual_seed(11)
+    p = _as_oracle(draw(m, 4, 400, gen, "cpu"))
+    f = O.eval_paths(p, gp.train_X)
+    assert (f - gp.train_Y[:, None]).abs().max() < 2e-2 * gp.y_std
+    assert p.G == (1 if draw is matheron_params else 4)
+
+
+def test_posterior_mean_params_match_oracle():
+    gp = make_gp(12, 3, noise=1e-3)
+    m = _model_from(gp)
+    X = torch.rand(20, 3, dtype=torch.float64)
+    p = _as_oracle(posterior_mean_params(m, "cpu"))
+    mean, _ = O.gp_posterior(gp, X)
+    np.testing.assert_allclose(O.eval_paths(p, X)[:, 0].numpy(), mean.numpy(), atol=1e-8)
+
+
+def test_gp_fit_runs_and_improves_mll():
+    gp = make_gp(20, 2, noise=1e-2)
+    m = SingleTaskGP(gp.train_X, gp.train_Y)
+    m.fit(max_iter=30)
+    assert torch.isfinite(m.covar_module.base_kernel.lengthscale).all()
+    assert float(m.likelihood.noise) >= 1e-4
+
+
+def test_product_fails_loudly_without_cuda():
+    from psbax_b200 import PsbaxError, SamplePathBatch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(PsbaxError):
+        SamplePathBatch(torch.zeros(1, 4, 2), torch.zeros(1, 4), torch.zeros(1, 4))
+
+
+def test_product_does_not_import_oracle():
+    import os
+    import re
+
+    from helpers import ROOT
+
+    pkg = os.path.join(ROOT, "psbax_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
