@@ -46,15 +46,16 @@ __device__ __forceinline__ EpiSmem epi_carve(float* base, int epi, int k) {
   return e;
 }
 
-__device__ __forceinline__ void epi_init(const EpiSmem& e, int epi, int k, int tid) {
+__device__ __forceinline__ void epi_init(const EpiSmem& e, int epi, int k, int tid,
+                                         int nthreads = NTHREADS) {
   if (epi == EPI_LEVELSET) {
-    for (int i = tid; i < TN; i += NTHREADS) {
+    for (int i = tid; i < TN; i += nthreads) {
       e.cnt[i] = 0u;
       e.mx[i] = -CUDART_INF_F;
       e.arg[i] = 0x7fffffff;
     }
   } else if (epi == EPI_TOPK) {
-    for (int i = tid; i < TN * k; i += NTHREADS) {
+    for (int i = tid; i < TN * k; i += nthreads) {
       e.tv[i] = -CUDART_INF_F;
       e.ti[i] = 0x7fffffff;
     }
@@ -87,14 +88,15 @@ __device__ __forceinline__ void topk_insert_warp(float* tv, int* ti, int k, floa
 // Epilogue over one staged tile.  sOut[sl * OUT_LD + r] holds the raw contraction
 // f (before the affine map) of local sample sl, tile row r.
 // ---------------------------------------------------------------------------------
-template <int EPI>
+// NW warps take part (tid in [0, 32 * NW)).
+template <int EPI, int NW = NWARPS>
 __device__ __forceinline__ void epilogue_tile(const KArgs& a, const float* sOut,
                                               const EpiSmem& e, int row0, int s0, int tid) {
   const int warp = tid >> 5, lane = tid & 31;
   const long long N = a.N;
   if constexpr (EPI == EPI_VALUES) {
     // lanes <-> samples so that global stores are contiguous along S
-    for (int r = warp; r < TM; r += NWARPS) {
+    for (int r = warp; r < TM; r += NW) {
       const long long row = (long long)row0 + r;
       if (row >= N) break;
 #pragma unroll
@@ -105,10 +107,10 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const float* sOut,
       }
     }
   } else {
-  // warp w owns local samples w*8 .. w*8+7; lanes <-> rows
+  // warp w owns local samples w*(TN/NW) .. ; lanes <-> rows
 #pragma unroll 1
-  for (int q = 0; q < TN / NWARPS; ++q) {
-    const int sl = warp * (TN / NWARPS) + q;
+  for (int q = 0; q < TN / NW; ++q) {
+    const int sl = warp * (TN / NW) + q;
     const int s = s0 + sl;
     if (s >= a.lay.S) break;
     if constexpr (EPI == EPI_LEVELSET) {
@@ -165,10 +167,11 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const float* sOut,
 
 // write the CTA's partial results: layout [gridDim.x][Sp] (+[k])
 template <int EPI>
-__device__ __forceinline__ void epilogue_flush(const KArgs& a, const EpiSmem& e, int s0, int tid) {
+__device__ __forceinline__ void epilogue_flush(const KArgs& a, const EpiSmem& e, int s0, int tid,
+                                               int nthreads = NTHREADS) {
   const int Sp = a.lay.Sp;
   if (EPI == EPI_LEVELSET) {
-    for (int sl = tid; sl < TN; sl += NTHREADS) {
+    for (int sl = tid; sl < TN; sl += nthreads) {
       const size_t o = (size_t)blockIdx.x * Sp + s0 + sl;
       a.p_cnt[o] = e.cnt[sl];
       a.p_max[o] = e.mx[sl];
@@ -176,7 +179,7 @@ __device__ __forceinline__ void epilogue_flush(const KArgs& a, const EpiSmem& e,
     }
   } else if (EPI == EPI_TOPK) {
     const int k = a.k;
-    for (int i = tid; i < TN * k; i += NTHREADS) {
+    for (int i = tid; i < TN * k; i += nthreads) {
       const int sl = i / k, q = i - sl * k;
       const size_t o = ((size_t)blockIdx.x * Sp + s0 + sl) * k + q;
       a.p_tv[o] = e.tv[i];

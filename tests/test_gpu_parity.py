@@ -41,13 +41,25 @@ def _tol(p):
     return (REL * O.path_scale(p)).numpy()
 
 
-@pytest.fixture(scope="module", params=CASES, ids=lambda c: "S%d_L%d_d%d_n%d_G%d_%s_N%d" % c)
+def _tensor_ok(c):
+    S, L, d, n, G, kernel, N = c
+    return G == 1 and S >= 16 and L > 0 and d <= 16
+
+
+ENGINE_CASES = [(c, "simt") for c in CASES] + [(c, "tensor") for c in CASES if _tensor_ok(c)]
+_REF_CACHE = {}
+
+
+@pytest.fixture(scope="module", params=ENGINE_CASES,
+                ids=lambda ce: "S%d_L%d_d%d_n%d_G%d_%s_N%d" % ce[0] + "_" + ce[1])
 def case(request):
-    S, L, d, n, G, kernel, N = request.param
+    (S, L, d, n, G, kernel, N), engine = request.param
     p = random_params(S, L, d, n, G=G, kernel=kernel, seed=S + L + d)
     X = candidates(N, d)
-    ref = O.eval_paths(p, X.double()).numpy()  # [N, S] float64
-    return p, X, ref, to_batch(p)
+    key = request.param[0]
+    if key not in _REF_CACHE:
+        _REF_CACHE[key] = O.eval_paths(p, X.double()).numpy()  # [N, S] float64
+    return p, X, _REF_CACHE[key], to_batch(p, engine=engine)
 
 
 def test_values(case):
@@ -122,11 +134,12 @@ def test_topk(case, k):
         assert set(sure.tolist()) <= set(idx[s].tolist())
 
 
-def test_ties_break_towards_smaller_index():
+@pytest.mark.parametrize("engine", ["simt", "tensor"])
+def test_ties_break_towards_smaller_index(engine):
     p = random_params(16, 64, 2, 8, seed=3)
     base = candidates(50, 2)
     X = torch.cat([base, base, base])  # every value appears three times, bit-identically
-    batch = to_batch(p)
+    batch = to_batch(p, engine=engine)
     val, idx = batch.topk(X.cuda(), 6)
     idx, val = idx.cpu().numpy(), val.cpu().numpy()
     for s in range(16):
@@ -137,7 +150,8 @@ def test_ties_break_towards_smaller_index():
     assert (am.cpu().numpy() == idx[:, 0]).all()
 
 
-def test_row_offset_and_sharded_merge_equal_whole():
+@pytest.mark.parametrize("engine", ["simt", "tensor"])
+def test_row_offset_and_sharded_merge_equal_whole(engine):
     """Shards of the candidate set + psbax_topk_merge == one launch over the whole set, bit for bit."""
     import ctypes as C
 
@@ -145,7 +159,7 @@ def test_row_offset_and_sharded_merge_equal_whole():
 
     p = random_params(64, 200, 3, 20, seed=9)
     X = candidates(5000, 3).cuda()
-    batch = to_batch(p)
+    batch = to_batch(p, engine=engine)
     k = 10
     val, idx = batch.topk(X, k)
     cuts = [0, 1300, 1301, 4000, 5000]
@@ -239,3 +253,29 @@ def test_errors_are_reported():
         batch.topk(X, 65)
     with pytest.raises(PsbaxError):
         batch.values(candidates(10, 3).cuda())
+
+
+def test_tensor_engine_many_tiles_matches_simt():
+    """Several tiles per persistent CTA (accumulator double-buffering, barrier phase wrap-around)
+    and several sample chunks: the tcgen05 engine against the FFMA engine and the oracle."""
+    p = random_params(100, 1000, 2, 64, seed=21)
+    N = 148 * 128 * 5 + 77
+    X = candidates(N, 2).cuda()
+    bt, bs = to_batch(p, engine="tensor"), to_batch(p, engine="simt")
+    vt, vs = bt.values(X), bs.values(X)
+    tol = torch.from_numpy(_tol(p)).cuda().float()
+    assert ((vt - vs).abs().max(0).values <= tol).all()
+    rows = torch.randperm(N)[:2048]
+    ref = O.eval_paths(p, X[rows].double().cpu()).numpy()
+    assert (np.abs(vt[rows].double().cpu().numpy() - ref).max(axis=0) <= _tol(p)).all()
+    tau = float(np.quantile(ref, 0.55))
+    rt, rs = bt.levelset(X, tau), bs.levelset(X, tau)
+    mt, ms = unpack_mask(rt.mask, N), unpack_mask(rs.mask, N)
+    undecided = ((vs - tau).abs() <= tol[None, :]).T.cpu().numpy()
+    assert ((mt != ms) <= undecided).all()
+    assert (rt.count.cpu().numpy() == mt.sum(1)).all()
+    tv, ti = bt.topk(X, 10)
+    sv, si = bs.topk(X, 10)
+    assert ((tv - sv).abs() <= tol[:, None]).all()
+    same = (ti == si).all(1).cpu().numpy()
+    assert same.mean() > 0.9  # near-ties between the engines may swap neighbours
