@@ -277,10 +277,11 @@ def run_ours(args):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        eng = paths_engine(paths)
         bf16 = peaks.get("bf16_tflops", 1590.0)
         which = "measured (MEASURED_PEAKS.json bf16_tflops burst)" if peaks else "fallback 1590 TF bf16"
-        # 3xTF32: TF32 dense = bf16 / 2; three MMAs per algorithmic FMA -> fp32-equivalent peak = bf16 / 6
-        peak_tf = bf16 / 6.0
+        # three MMAs per algorithmic FMA.  BF16x3: peak = bf16 / 3;  3xTF32: TF32 dense = bf16 / 2 -> bf16 / 6
+        peak_tf = bf16 / (3.0 if eng == "tensor_bf16x3" else 6.0)
         flops_launch = 2.0 * (L + NTRAIN) * S * N  # algorithmic, per launch (per GPU)
         kern_s = (t_kern / K)
         achieved = flops_launch / kern_s / 1e12
@@ -302,8 +303,9 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (3xTF32 tensor contraction)" if paths_engine(paths) == "tensor" else "f32",
-            "data": "synthetic", "config": dict(workload_config(world), engine=paths_engine(paths)),
+            "vs_baseline": None, "dtype": {"simt": "f32", "tensor_tf32x3": "f32 (3xTF32 split, fp32 accumulate)",
+                                           "tensor_bf16x3": "f32 (BF16x3 split, fp32 accumulate)"}[eng],
+            "data": "synthetic", "config": dict(workload_config(world), engine=eng),
             "e2e": {"value": evals_step * K / t_e2e_max, "unit": UNIT,
                     "h2d_bytes_per_step": N * D * 4, "d2h_bytes_per_step": S * words * 4 + S * 16,
                     "ms_per_step": 1e3 * t_e2e_max / K},
@@ -313,7 +315,8 @@ def run_ours(args):
                          "kernel": "fused evaluate+level-set kernel (+3 us finalize)",
                          "kernel_ms": 1e3 * kern_s,
                          "note": (f"algorithmic flops = 2*(L+n)*S per candidate = {2 * (L + NTRAIN) * S}; "
-                                  f"peak = bf16 {bf16} TF/s / 6 (TF32 = bf16/2, 3xTF32 issues 3 MMAs), {which}")},
+                                  f"peak = bf16 {bf16} TF/s / {3 if eng == 'tensor_bf16x3' else 6} "
+                                  f"(three split-product MMAs per algorithmic FMA; TF32 runs at bf16/2), {which}")},
             "cpu_baseline": cpu,
             "clocks": clk,
             "wall_ms_per_step": 1e3 * t_wall_max / K,
@@ -328,17 +331,14 @@ def run_ours(args):
 
 
 def paths_engine(paths):
-    """Which kernel family the library resolved to for this batch (mirrors make_layout)."""
-    import ctypes as C
-
-    from psbax_b200 import _lib
-
-    if paths.engine != "simt" and paths.G == 1 and paths.S >= 16 and paths.L > 0:
-        st = _lib.PathsStruct.from_buffer_copy(bytes(paths._struct))
-        st.engine = 2
-        n = C.c_size_t(0)
-        if _lib.load().psbax_pack_bytes(C.byref(st), C.byref(n)) == 0:
-            return "tensor"
+    """Which kernel family the library resolves to for this batch (mirrors make_layout)."""
+    shared = paths.G == 1 and paths.S >= 16 and paths.L > 0
+    if paths.engine == "simt" or not shared:
+        return "simt"
+    if paths.engine == "tensor":
+        return "tensor_tf32x3"
+    if paths.engine == "tensor_bf16" or paths.d <= 16:
+        return "tensor_bf16x3"
     return "simt"
 
 
@@ -348,7 +348,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tensor"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tensor", "tensor_bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -53,10 +53,12 @@ enum { /* psbax_paths_t.kernel */
   PSBAX_KERNEL_MATERN52 = 3
 };
 
-enum { /* psbax_paths_t.engine: which kernel family evaluates a shared basis */
+enum { /* psbax_paths_t.engine: which kernel family evaluates a shared basis.  AUTO picks
+        * TENSOR_BF16 when the shape allows (G == 1, S >= 16, L > 0, d <= 16), else SIMT. */
   PSBAX_ENGINE_AUTO = 0,
   PSBAX_ENGINE_SIMT = 1,   /* FFMA + MUFU kernels */
-  PSBAX_ENGINE_TENSOR = 2  /* tcgen05 3xTF32 kernel (G == 1 only) */
+  PSBAX_ENGINE_TENSOR = 2,      /* tcgen05 kernel, 3xTF32 operand split (G == 1 only) */
+  PSBAX_ENGINE_TENSOR_BF16 = 3  /* tcgen05 kernel, BF16x3 operand split (G == 1 only) */
 };
 
 /* The S sample paths.  Replaces the closure `get_gp_samples` returns
@@ -86,6 +88,11 @@ int psbax_version(void);
 
 /* Copies the calling thread's last error message (NUL-terminated) into buf. */
 int psbax_last_error(char* buf, size_t len);
+
+/* Profiling aid (not used by the product path): when set to a device buffer of at least
+ * 4 * 128 * 8 int64, CTA 0 of the tensor-engine kernel records clock64() time stamps of its
+ * pipeline stages there; NULL (the default) disables tracing. */
+int psbax_debug_trace_buffer(void* device_buffer);
 
 /* Number of SMs of the current device (sizes persistent grids / workspaces). */
 int psbax_device_sms(int* sms);

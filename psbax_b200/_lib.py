@@ -11,14 +11,14 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpsbax_b200.so")
+LIB_PATH = os.environ.get("PSBAX_LIB") or os.path.join(_HERE, "libpsbax_b200.so")
 
 KERNEL_IDS = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3}
-ENGINE_IDS = {"auto": 0, "simt": 1, "tensor": 2}
+ENGINE_IDS = {"auto": 0, "simt": 1, "tensor": 2, "tensor_bf16": 3}
 
 # every symbol include/psbax_b200.h declares
 EXPORTS = [
-    "psbax_version", "psbax_last_error", "psbax_device_sms", "psbax_pack_bytes", "psbax_pack",
+    "psbax_version", "psbax_last_error", "psbax_debug_trace_buffer", "psbax_device_sms", "psbax_pack_bytes", "psbax_pack",
     "psbax_workspace_bytes", "psbax_eval_values", "psbax_eval_levelset", "psbax_eval_topk",
     "psbax_topk_merge", "psbax_subset_select", "psbax_eval_grad",
 ]
@@ -50,6 +50,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.psbax_version.restype = C.c_int
     lib.psbax_version.argtypes = []
     lib.psbax_last_error.argtypes = [C.c_char_p, sz]
+    lib.psbax_debug_trace_buffer.argtypes = [vp]
     lib.psbax_device_sms.argtypes = [C.POINTER(C.c_int)]
     lib.psbax_pack_bytes.argtypes = [P, C.POINTER(sz)]
     lib.psbax_pack.argtypes = [P, vp, sz, vp]

@@ -32,17 +32,21 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True builds libpsbax_b200_trace.so with the clock64 pipeline trace compiled in
+    (profiling aid; select it with PSBAX_LIB=<path>)."""
+    out = OUT.replace(".so", "_trace.so") if trace else OUT
+    if not force and not trace and not _stale():
         return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-DPSBAX_TC_TRACE=1"] if trace else []) + \
+        (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libpsbax_b200.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv))

@@ -2,6 +2,7 @@
 // Host side: argument validation, operand-pack layout, launch configuration.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sp_common.cuh"
@@ -14,6 +15,7 @@ using namespace psbax;
 namespace {
 
 thread_local char g_err[512] = "";
+long long* g_trace = nullptr;  // profiling aid, see psbax_debug_trace_buffer
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -52,9 +54,9 @@ int validate(const psbax_paths_t* p) {
     return fail(PSBAX_E_INVALID, "omega / bias / W must be non-NULL when L > 0");
   if (p->n > 0 && (!p->Xtrain || !p->inv_ls || !p->V))
     return fail(PSBAX_E_INVALID, "Xtrain / inv_ls / V must be non-NULL when n > 0");
-  if (p->engine < PSBAX_ENGINE_AUTO || p->engine > PSBAX_ENGINE_TENSOR)
+  if (p->engine < PSBAX_ENGINE_AUTO || p->engine > PSBAX_ENGINE_TENSOR_BF16)
     return fail(PSBAX_E_INVALID, "unknown engine id %d", p->engine);
-  if (p->engine == PSBAX_ENGINE_TENSOR && !tensor_supported(p))
+  if ((p->engine == PSBAX_ENGINE_TENSOR || p->engine == PSBAX_ENGINE_TENSOR_BF16) && !tensor_supported(p))
     return fail(PSBAX_E_UNSUPPORTED,
                 "tensor engine needs a shared basis (G == 1), d <= %d and S <= %d (got G=%d d=%d S=%d)",
                 TC_MAX_D, TC_MAX_S, p->G, p->d, p->S);
@@ -72,8 +74,9 @@ Layout make_layout(const psbax_paths_t* p) {
   l.Sp = round_up(p->S, TN);
   const bool shared = (p->G == 1) && (p->S >= 16) && (p->L > 0);
   if (!shared) l.mode = MODE_PERSAMPLE;
-  else if (p->engine == PSBAX_ENGINE_TENSOR || (p->engine == PSBAX_ENGINE_AUTO && tensor_supported(p)))
-    l.mode = MODE_TENSOR;
+  else if (p->engine == PSBAX_ENGINE_TENSOR) l.mode = MODE_TENSOR;
+  else if (p->engine == PSBAX_ENGINE_TENSOR_BF16 || (p->engine == PSBAX_ENGINE_AUTO && tensor_supported(p)))
+    l.mode = MODE_TENSOR_BF16;  // AUTO: the faster split; both hold the 1e-4 contract
   else l.mode = MODE_SHARED_SIMT;
   l.Lp_ft = (l.mode == MODE_PERSAMPLE) ? 0 : l.Lp;
   l.Kp = round_up(l.Lp_ft + l.np_, TK);
@@ -83,7 +86,7 @@ Layout make_layout(const psbax_paths_t* p) {
   l.off_wv = off;    off += (size_t)l.Kp * l.Sp;
   l.off_pb = off;    if (l.mode == MODE_PERSAMPLE) off += (size_t)l.S * l.Lp * l.OSB;
   off = (off + 63) / 64 * 64;  // 256-byte alignment for the tensor operands
-  l.off_tc = off;    if (l.mode == MODE_TENSOR) off += tensor_pack_floats(l);
+  l.off_tc = off;    if (is_tensor_mode(l.mode)) off += tensor_pack_floats(l);
   l.total_floats = off;
   return l;
 }
@@ -171,6 +174,8 @@ int prepare(const psbax_paths_t* p, const void* pack, const float* X, int64_t N,
   a.N = N;
   a.ystd = p->y_std;
   a.c0 = (float)((double)p->y_std * (double)p->mean_const + (double)p->y_mean);
+  if (const char* dbg = getenv("PSBAX_TC_DEBUG")) a.debug = atoi(dbg);
+  a.trace = g_trace;
   int gx, gy, nt;
   grid_for(a.lay, N, out->sms, &gx, &gy, &nt);
   a.ntiles = nt;
@@ -188,6 +193,11 @@ int psbax_last_error(char* buf, size_t len) {
   if (!buf || len == 0) return PSBAX_E_INVALID;
   strncpy(buf, g_err, len - 1);
   buf[len - 1] = 0;
+  return PSBAX_OK;
+}
+
+int psbax_debug_trace_buffer(void* device_buffer) {
+  g_trace = static_cast<long long*>(device_buffer);
   return PSBAX_OK;
 }
 
@@ -216,7 +226,7 @@ int psbax_pack(const psbax_paths_t* paths, void* pack, size_t pack_bytes, void* 
   k_pack<<<296, 256, 0, st>>>(l, paths->omega, paths->bias, paths->W, paths->Xtrain,
                               paths->inv_ls, paths->V, static_cast<float*>(pack));
   CUDA_TRY(cudaGetLastError());
-  if (l.mode == MODE_TENSOR) {
+  if (is_tensor_mode(l.mode)) {
     rc = tensor_pack(l, static_cast<float*>(pack), st);
     if (rc) return fail(rc, "tensor operand pack failed");
   }
@@ -235,7 +245,7 @@ int psbax_workspace_bytes(const psbax_paths_t* paths, int64_t N, int32_t k, size
   const Layout l = make_layout(paths);
   int gx, gy, nt;
   grid_for(l, N, sms, &gx, &gy, &nt);
-  if (l.mode == MODE_TENSOR) gx = tensor_parts(l, N, sms);
+  if (is_tensor_mode(l.mode)) gx = tensor_parts(l, N, sms);
   const size_t per = (size_t)gx * l.Sp;
   const size_t ls = per * (sizeof(unsigned int) + sizeof(float) + sizeof(int));
   const size_t tk = per * (size_t)(k > 0 ? k : 1) * (sizeof(float) + sizeof(int));
@@ -253,7 +263,7 @@ int psbax_eval_values(const psbax_paths_t* paths, const void* pack, const float*
   pr.a.out = out;
   pr.a.ld_out = ld_out;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (pr.a.lay.mode == MODE_TENSOR) return tensor_launch(EPI_VALUES, pr.a, pr.sms, st, g_err, sizeof(g_err));
+  if (is_tensor_mode(pr.a.lay.mode)) return tensor_launch(EPI_VALUES, pr.a, pr.sms, st, g_err, sizeof(g_err));
   return dispatch_simt<EPI_VALUES>(pr.a, pr.grid, st);
 }
 
@@ -273,7 +283,7 @@ int psbax_eval_levelset(const psbax_paths_t* paths, const void* pack, const floa
     return fail(PSBAX_E_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
   KArgs& a = pr.a;
   const Layout& l = a.lay;
-  const int parts = (l.mode == MODE_TENSOR) ? tensor_parts(l, N, pr.sms) : (int)pr.grid.x;
+  const int parts = is_tensor_mode(l.mode) ? tensor_parts(l, N, pr.sms) : (int)pr.grid.x;
   const size_t per = (size_t)parts * l.Sp;
   a.row_offset = row_offset;
   a.tau = tau;
@@ -283,7 +293,7 @@ int psbax_eval_levelset(const psbax_paths_t* paths, const void* pack, const floa
   a.p_max = reinterpret_cast<float*>(a.p_cnt + per);
   a.p_arg = reinterpret_cast<int*>(a.p_max + per);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (l.mode == MODE_TENSOR) rc = tensor_launch(EPI_LEVELSET, a, pr.sms, st, g_err, sizeof(g_err));
+  if (is_tensor_mode(l.mode)) rc = tensor_launch(EPI_LEVELSET, a, pr.sms, st, g_err, sizeof(g_err));
   else rc = dispatch_simt<EPI_LEVELSET>(a, pr.grid, st);
   if (rc) return rc;
   k_levelset_finalize<<<(l.S + 127) / 128, 128, 0, st>>>(a.p_cnt, a.p_max, a.p_arg, parts, l.Sp, l.S,
@@ -309,14 +319,14 @@ int psbax_eval_topk(const psbax_paths_t* paths, const void* pack, const float* X
     return fail(PSBAX_E_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
   KArgs& a = pr.a;
   const Layout& l = a.lay;
-  const int parts = (l.mode == MODE_TENSOR) ? tensor_parts(l, N, pr.sms) : (int)pr.grid.x;
+  const int parts = is_tensor_mode(l.mode) ? tensor_parts(l, N, pr.sms) : (int)pr.grid.x;
   const size_t per = (size_t)parts * l.Sp * k;
   a.row_offset = row_offset;
   a.k = k;
   a.p_tv = static_cast<float*>(workspace);
   a.p_ti = reinterpret_cast<int*>(a.p_tv + per);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (l.mode == MODE_TENSOR) rc = tensor_launch(EPI_TOPK, a, pr.sms, st, g_err, sizeof(g_err));
+  if (is_tensor_mode(l.mode)) rc = tensor_launch(EPI_TOPK, a, pr.sms, st, g_err, sizeof(g_err));
   else rc = dispatch_simt<EPI_TOPK>(a, pr.grid, st);
   if (rc) return rc;
   k_topk_merge<int><<<l.S, 128, 0, st>>>(a.p_tv, a.p_ti, parts, l.Sp, k, row_offset, out_val,

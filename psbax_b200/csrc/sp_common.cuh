@@ -17,7 +17,7 @@ constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 
 enum { EPI_VALUES = 0, EPI_LEVELSET = 1, EPI_TOPK = 2 };
-enum { MODE_PERSAMPLE = 0, MODE_SHARED_SIMT = 1, MODE_TENSOR = 2 };
+enum { MODE_PERSAMPLE = 0, MODE_SHARED_SIMT = 1, MODE_TENSOR = 2, MODE_TENSOR_BF16 = 3 };
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -66,6 +66,8 @@ struct KArgs {
   int k;
   float* p_tv;
   int* p_ti;
+  int debug;  // PSBAX_TC_DEBUG bit mask (profiling experiments only; 0 in production)
+  long long* trace;  // optional device buffer for clock64 traces (psbax_debug_trace_buffer)
 };
 
 // ---------------------------------------------------------------------------------
@@ -97,6 +99,30 @@ __device__ __forceinline__ float kernel_profile(float r2, int kernel) {
     return (1.0f + s) * fast_ex2(-LOG2E * s);
   }
   return fast_ex2(-LOG2E * r);
+}
+
+// eight profiles at once: one (warp-uniform) switch, straight-line bodies
+__device__ __forceinline__ void kernel_profile8(const float (&r2)[8], float (&v)[8], int kernel) {
+  constexpr float LOG2E = 1.4426950408889634f;
+  if (kernel == PSBAX_KERNEL_MATERN52) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = 2.2360679774997896f * fast_sqrt(r2[j]);
+      v[j] = (1.0f + s + 1.6666666666666667f * r2[j]) * fast_ex2(-LOG2E * s);
+    }
+  } else if (kernel == PSBAX_KERNEL_RBF) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fast_ex2(-0.5f * LOG2E * r2[j]);
+  } else if (kernel == PSBAX_KERNEL_MATERN32) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = 1.7320508075688772f * fast_sqrt(r2[j]);
+      v[j] = (1.0f + s) * fast_ex2(-LOG2E * s);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fast_ex2(-LOG2E * fast_sqrt(r2[j]));
+  }
 }
 
 // d kappa / d(r2) * 2  (so that grad_x = dk2 * diff * inv_ls), used by the gradient kernel

@@ -212,6 +212,51 @@ __device__ __forceinline__ float kern_r2(const float* __restrict__ ft, const flo
   return r2;
 }
 
+// a table row of OSV floats (multiple of 4) as 128-bit shared-memory loads
+template <int OSV>
+__device__ __forceinline__ void load_row(const float* __restrict__ ft, float (&w)[OSV]) {
+#pragma unroll
+  for (int v = 0; v < OSV / 4; ++v) {
+    const float4 q = *reinterpret_cast<const float4*>(ft + 4 * v);
+    w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+  }
+}
+
+// Same, with the table row fetched as 128-bit shared-memory loads (row stride and base are
+// multiples of 16 bytes).
+template <int DP>
+__device__ __forceinline__ float rff_arg_v4(const float* __restrict__ ft, const float (&x)[DP]) {
+  constexpr int NV = (DP + 1 + 3) / 4;
+  float r[NV * 4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 q = *reinterpret_cast<const float4*>(ft + 4 * v);
+    r[4 * v] = q.x; r[4 * v + 1] = q.y; r[4 * v + 2] = q.z; r[4 * v + 3] = q.w;
+  }
+  float arg = r[DP];
+#pragma unroll
+  for (int i = 0; i < DP; ++i) arg = fmaf(x[i], r[i], arg);
+  return arg;
+}
+
+template <int DP>
+__device__ __forceinline__ float kern_r2_v4(const float* __restrict__ ft, const float (&xs)[DP]) {
+  constexpr int NV = (DP + 3) / 4;
+  float r[NV * 4];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float4 q = *reinterpret_cast<const float4*>(ft + 4 * v);
+    r[4 * v] = q.x; r[4 * v + 1] = q.y; r[4 * v + 2] = q.z; r[4 * v + 3] = q.w;
+  }
+  float r2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < DP; ++i) {
+    const float df = xs[i] + r[i];
+    r2 = fmaf(df, df, r2);
+  }
+  return r2;
+}
+
 // ---------------------------------------------------------------------------------
 // Kernel A: shared basis, SIMT contraction
 //   grid = (gx persistent CTAs, Sp / 64 sample chunks), block = 256

@@ -1,28 +1,36 @@
 // tcgen05 engine: shared-basis sample paths as a 3xTF32 tensor-core contraction whose
 // A operand (the RFF / kernel features) is generated on the fly and never leaves the SM.
 //
-// One persistent CTA per SM, 16 warps, warp-specialised:
-//   warp 0      B loader   : bulk-async copies (cp.async.bulk, TMA unit) of 16 KB blocks of the
+// One persistent CTA per SM, 24 warps, warp-specialised:
+//   warp 21     B loader   : bulk-async copies (cp.async.bulk, TMA unit) of 16 KB blocks of the
 //                            hi/lo-split [W;V] operand, pre-laid-out in UMMA canonical K-major
 //                            form by tensor_pack(), into a 4-stage shared-memory ring
-//   warp 1      MMA issuer : one thread issues tcgen05.mma kind::tf32, A from TENSOR MEMORY,
+//   warp 20     MMA issuer : one thread issues tcgen05.mma kind::tf32, A from TENSOR MEMORY,
 //                            B from shared memory, fp32 accumulators in tensor memory
-//   warp 2      TMEM allocator
-//   warps 4-11  producers  : lane = candidate row (x in registers).  Per 32-feature block each
-//                            thread evaluates 16 features (FFMA projection + MUFU cos, or the
+//   warp 22     TMEM allocator
+//   warps 0-15  producers  : lane = candidate row (x in registers).  Per 32-feature block each
+//                            thread evaluates 8 features (FFMA projection + MUFU cos, or the
 //                            Matern/RBF profile), splits them into TF32 hi/lo and writes them
 //                            straight into the A stage in tensor memory (tcgen05.st)
-//   warps 12-15 epilogue   : tcgen05.ld the finished 128 x 64 tile, stage it in shared memory
+//   warps 16-19 epilogue   : tcgen05.ld the finished 128 x 64 tile, stage it in shared memory
 //                            and run the same fused reduction as the SIMT kernels (level-set
 //                            ballots / top-k filter / values dump) while the next tile's MMAs run
 //
-// 3xTF32:  f = Phi_hi*W_hi + Phi_hi*W_lo + Phi_lo*W_hi  (fp32 accumulate), issued as
-//   MMA1: A = Phi_hi, B = [W_hi | W_lo]  (N = 128)  -> D[:, 0:128]
-//   MMA2: A = Phi_lo, B =  W_hi          (N =  64)  -> D[:, 0:64]  (accumulate)
-// and the epilogue adds D[:, s] + D[:, 64 + s].
+// Split precision, fp32 accumulate: f = Phi_1*W_1 + Phi_1*W_2 + Phi_2*W_1, three M=128, N=64 MMAs
+// per k-step into the same 64 accumulator columns.  Two operand formats:
+//   3xTF32  (PSBAX_ENGINE_TENSOR)      x = hi + lo, hi = TF32(x): ~2^-21 per product; K=8 per MMA
+//   BF16x3  (PSBAX_ENGINE_TENSOR_BF16) x = x1 + x2, x1 = bf16(x), x2 = bf16(x - x1): <= 3*2^-18 per
+//           product (6x inside the 1e-4 tolerance); K=16 per MMA at the same cycles, half the
+//           operand bytes in shared and tensor memory -> 4 A stages instead of 2.
 //
-// Tensor-memory columns (512 allocated): D0 [0,128) D1 [128,256) | A stage s: hi [256+64s, +32),
-// lo [288+64s, +32).
+// A CTA pass covers TWO 128-row tiles (256 candidates) against every [W;V] block: each table
+// row read from shared memory and each B block serve two evaluations, and the per-block
+// synchronisation is amortised over 24 MMAs.
+//
+// Tensor-memory columns (512 allocated):
+//   D[buf][tile]     : (buf*2 + tile)*64               buf, tile in {0,1}  (accumulators, double-buffered)
+//   A[stage][tile]   : 256 + (stage*2 + tile)*ACT      first split at +0, second at +ACT/2
+//                      ACT = 64 (TF32, 2 stages) or 32 (BF16 pairs, 4 stages)
 #pragma once
 #include "sp_common.cuh"
 #include "sp_simt.cuh"
@@ -31,20 +39,57 @@ namespace psbax {
 
 constexpr int TC_MAX_D = 16;
 constexpr int TC_MAX_S = 1 << 20;  // any S: processed in chunks of 64 samples
-constexpr int TC_THREADS = 512;
-constexpr int TC_NSB = 4;                    // B stages
-constexpr int TC_BBYTES = 128 * TK * 4;      // 16 KB per stage: 128 rows (hi|lo) x 32 k
-constexpr int TC_PROD_WARP0 = 4, TC_NPROD = 8;
-constexpr int TC_EPI_WARP0 = 12, TC_NEPI = 4;
+#ifndef PSBAX_TC_NPROD
+#define PSBAX_TC_NPROD 16
+#endif
+template <bool BF>
+struct TcCfg;
+template <>
+struct TcCfg<false> {  // 3xTF32
+  static constexpr int NSB = 4, NSA = 2;           // B (smem) and A (tmem) ring depths
+  static constexpr int BBYTES = 128 * TK * 4;      // 16 KB: 128 rows (split1|split2) x 32 k
+  static constexpr int ACT = 64;                   // A columns per tile per stage
+  static constexpr int KSTEPS = TK / 8;            // MMAs along k per block (K = 8)
+  static constexpr int KCOLS = 8;                  // A columns per k-step
+  static constexpr int B_KSTEP = 256;              // bytes: two 128-byte core matrices per k-step
+  static constexpr int B_SBO = 1024;               // bytes between 8-row groups
+  static constexpr int B_SPLIT2 = 8 * B_SBO;       // rows 64..127
+  static constexpr int WCOLS = 8;                  // A columns per 8 features per split
+};
+template <>
+struct TcCfg<true> {  // BF16x3
+  static constexpr int NSB = 8, NSA = 4;
+  static constexpr int BBYTES = 128 * TK * 2;      // 8 KB
+  static constexpr int ACT = 32;
+  static constexpr int KSTEPS = TK / 16;           // K = 16
+  static constexpr int KCOLS = 8;
+  static constexpr int B_KSTEP = 256;
+  static constexpr int B_SBO = 512;
+  static constexpr int B_SPLIT2 = 8 * B_SBO;
+  static constexpr int WCOLS = 4;                  // 8 bf16 features = 4 packed columns
+};
+// warp roles.  The issue arbiter favours high warp ids (measured: epilogue warps placed BELOW the
+// producers were starved to ~5% IPC and became the critical path).  Bounded-work roles sit on
+// top: MMA issuer and loader (mostly parked), then the epilogue, the producers at the bottom.
+constexpr int TC_PROD_WARP0 = 0, TC_NPROD = PSBAX_TC_NPROD;          // 8 or 16 producer warps
+constexpr int TC_EPI_WARP0 = TC_NPROD, TC_NEPI = 4;
+constexpr int TC_WARP_MMA = TC_EPI_WARP0 + TC_NEPI, TC_WARP_LOAD = TC_WARP_MMA + 1,
+              TC_WARP_ALLOC = TC_WARP_MMA + 2;
+constexpr int TC_THREADS = (TC_WARP_MMA + 4) * 32;
+constexpr int TC_FPW = TK / (TC_NPROD / 4);                            // features per producer warp per block
+static_assert(TC_NPROD == 8 || TC_NPROD == 16, "8 or 16 producer warps");
 constexpr int TC_COL_D = 0, TC_COL_A = 256;
+constexpr int TC_TILES = 2;                  // row tiles per CTA pass
 constexpr uint32_t TC_TMEM_COLS = 512;
 
 inline bool tensor_supported(const psbax_paths_t* p) {
   return p->G == 1 && p->S >= 16 && p->L > 0 && p->d <= TC_MAX_D;
 }
-// [chunks][nkb] images of 16 KB
+inline bool is_tensor_mode(int mode) { return mode == MODE_TENSOR || mode == MODE_TENSOR_BF16; }
+// [chunks][nkb] images of BBYTES
 inline size_t tensor_pack_floats(const Layout& l) {
-  return (size_t)(l.Sp / TN) * (l.Kp / TK) * (TC_BBYTES / 4);
+  const size_t bb = (l.mode == MODE_TENSOR_BF16) ? TcCfg<true>::BBYTES : TcCfg<false>::BBYTES;
+  return (size_t)(l.Sp / TN) * (l.Kp / TK) * (bb / 4);
 }
 
 // ---------------------------------------------------------------------------------
@@ -63,11 +108,35 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// try_wait: the hardware parks the thread for a bounded time and wakes it when the phase
+// completes (PSBAX_TC_WAIT_HINT adds an explicit suspend-time hint, in ns).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if defined(PSBAX_TC_WAIT_HINT)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)PSBAX_TC_WAIT_HINT)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
+  return ok != 0;
+}
+// non-blocking probe (no suspend): issued early so that its latency overlaps with compute
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
@@ -80,6 +149,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) asm volatile("trap;");
   }
+}
+// one lane of a converged warp; the compiler then issues uniform-datapath instructions
+// (UTCHMMA, UBLKCP, UTCBAR) directly instead of wrapping each in an elect loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// one lane polls, the warp follows: 32 lanes hitting the same mbarrier word serialise in the
+// shared-memory sync unit (measured: a dominant per-block cost with 16 producer warps)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -107,6 +193,26 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3])
+               : "memory");
+}
+// {hi16, lo16} = {bf16(a), bf16(b)}, round to nearest even
+__device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b));
+  return d;
+}
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
@@ -114,6 +220,11 @@ __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16])
       "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
       "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -136,38 +247,53 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lb
   d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100)
   return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
-// instruction descriptor: TF32 x TF32 -> F32, both operands K-major, M = 128
+// instruction descriptor: (TF32 x TF32 | BF16 x BF16) -> F32, both operands K-major, M = 128
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// clock trace (compile with -DPSBAX_TC_TRACE=1): role r (0 = MMA, 1 = first producer warp,
+// 2 = first epilogue warp, 3 = loader), CTA 0 only.  Compiled out of the production build.
+#if defined(PSBAX_TC_TRACE) && PSBAX_TC_TRACE
+#define TC_TRACE(role, it, slot)                                                         \
+  do {                                                                                   \
+    if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (it) < 128)          \
+      a.trace[((role) * 128 + (it)) * 8 + (slot)] = clock64();                           \
+  } while (0)
+#else
+#define TC_TRACE(role, it, slot) do { } while (0)
+#endif
 
 struct TcSmem {
-  // offsets in bytes from the 1024-aligned dynamic smem base
-  uint32_t b, ft, out, state, il, bars, total;
+  uint32_t b, ft, out, state, il, bars, total;  // byte offsets into dynamic shared memory
 };
 __host__ __device__ inline TcSmem tc_smem_layout(const Layout& l, int epi, int k) {
+  const bool bf = l.mode == MODE_TENSOR_BF16;
   TcSmem s{};
   uint32_t o = 0;
-  s.b = o;     o += TC_NSB * TC_BBYTES;
+  s.b = o;     o += bf ? TcCfg<true>::NSB * TcCfg<true>::BBYTES : TcCfg<false>::NSB * TcCfg<false>::BBYTES;
   s.ft = o;    o += (uint32_t)l.Kp * l.OS * 4;
   s.out = o;   o += TN * OUT_LD * 4;
   s.state = o; o += (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;
   s.il = o;    o += (uint32_t)round_up(l.dp4, 4) * 4;
   o = (o + 15) / 16 * 16;
   s.bars = o;  o += 32 * 8;
-  s.total = o + 1024;  // slack for the manual 1024-byte alignment
+  s.total = o;
   return s;
 }
 
-// CTA c of gx handles the contiguous tile range [t0, t1)
-__host__ __device__ inline void tc_tile_range(int ntiles, int gx, int c, int* t0, int* t1) {
-  const int base = ntiles / gx, rem = ntiles % gx;
+// CTA c of gx handles the contiguous range [t0, t1) of passes
+__host__ __device__ inline void tc_tile_range(int n, int gx, int c, int* t0, int* t1) {
+  const int base = n / gx, rem = n % gx;
   *t0 = c * base + (c < rem ? c : rem);
   *t1 = *t0 + base + (c < rem ? 1 : 0);
 }
 
 inline int tensor_parts(const Layout& l, long long N, int sms) {
-  const long long nt = (N + TM - 1) / TM;
+  const long long nt = (N + TC_TILES * TM - 1) / (TC_TILES * TM);  // passes of 256 rows
   const int gy = l.Sp / TN;
   long long gx = (sms + gy - 1) / gy;
   if (gx > nt) gx = nt;
@@ -176,26 +302,46 @@ inline int tensor_parts(const Layout& l, long long N, int sms) {
 }
 
 // ---------------------------------------------------------------------------------
-// operand pack: hi/lo TF32 split of [W;V] in UMMA canonical (no-swizzle, K-major) layout
-//   image(cy, kb)[row r in 0..127][k in 0..31]:  r < 64: hi(wv[kb*32+k][cy*64+r]),
-//                                                r >= 64: lo(wv[kb*32+k][cy*64+r-64])
-//   float offset inside the image: (r/8)*256 + (k/4)*32 + (r%8)*4 + (k%4)
+// operand pack: the two splits of [W;V] in UMMA canonical (no-swizzle, K-major) layout.
+//   image(cy, kb)[row r in 0..127][k in 0..31]:  r < 64: split1(wv[kb*32+k][cy*64+r]),
+//                                                r >= 64: split2(wv[kb*32+k][cy*64+r-64])
+//   core matrix = 8 rows x 16 bytes, stored contiguously (128 B); K-adjacent core matrices 128 B
+//   apart (LBO); 8-row groups SBO apart.  Element offset inside an image:
+//     TF32: (r/8)*256 + (k/4)*32 + (r%8)*4 + (k%4)      (floats)
+//     BF16: (r/8)*256 + (k/8)*64 + (r%8)*8 + (k%8)      (bf16)
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t bf16_rn_bits(float x) { return (uint16_t)(cvt_bf16x2(x, x) & 0xffffu); }
+
 __global__ void k_tensor_pack(Layout lay, float* __restrict__ pack) {
   const float* __restrict__ wv = pack + lay.off_wv;
-  float* __restrict__ tc = pack + lay.off_tc;
   const int nkb = lay.Kp / TK;
   const size_t total = (size_t)(lay.Sp / TN) * nkb * 4096;
+  const bool bf = lay.mode == MODE_TENSOR_BF16;
+  float* __restrict__ tc32 = pack + lay.off_tc;
+  uint16_t* __restrict__ tc16 = reinterpret_cast<uint16_t*>(pack + lay.off_tc);
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int within = (int)(idx & 4095);
     const size_t img = idx >> 12;
     const int kb = (int)(img % nkb), cy = (int)(img / nkb);
-    const int rg = within >> 8, kc = (within >> 5) & 7, r8 = (within >> 2) & 7, k4 = within & 3;
-    const int r = rg * 8 + r8, k = kc * 4 + k4;
+    const int rg = within >> 8;
+    int r, k;
+    if (bf) {
+      r = rg * 8 + ((within >> 3) & 7);
+      k = ((within >> 6) & 3) * 8 + (within & 7);
+    } else {
+      r = rg * 8 + ((within >> 2) & 7);
+      k = ((within >> 5) & 7) * 4 + (within & 3);
+    }
     const float x = wv[(size_t)(kb * TK + k) * lay.Sp + cy * TN + (r & 63)];
-    const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);  // round to TF32
-    tc[idx] = (r < 64) ? hi : (x - hi);
+    if (bf) {
+      const uint16_t b1 = bf16_rn_bits(x);
+      const float x1 = __uint_as_float((uint32_t)b1 << 16);
+      tc16[idx] = (r < 64) ? b1 : bf16_rn_bits(x - x1);
+    } else {
+      const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);  // round to TF32
+      tc32[idx] = (r < 64) ? hi : (x - hi);
+    }
   }
 }
 
@@ -205,14 +351,86 @@ inline int tensor_pack(const Layout& l, float* pack, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------
+// Level-set epilogue with register-resident state.  The epilogue warps are on the critical
+// path of the tensor engine (4 warps serve a 256-row pass), so: lane = row, every lane keeps its
+// own running max per sample, the cross-lane arg-max reduction happens once per kernel, the
+// 16 x 4 (sample, row-group) steps are fully unrolled (independent chains), and the four mask
+// words of a sample leave as one 16-byte store.
+// ---------------------------------------------------------------------------------
+template <int NW>
+struct LsRegState {
+  static constexpr int SPW = TN / NW;  // samples per warp
+  float bv[SPW];
+  int bi[SPW];
+  unsigned int cnt[SPW];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int q = 0; q < SPW; ++q) { bv[q] = -CUDART_INF_F; bi[q] = 0x7fffffff; cnt[q] = 0u; }
+  }
+};
+
+template <int NW>
+__device__ __forceinline__ void epilogue_levelset_reg(const KArgs& a, const float* sOut, LsRegState<NW>& st,
+                                                      int row0, int s0, int tid) {
+  constexpr int SPW = TN / NW;
+  const int warp = tid >> 5, lane = tid & 31;
+  const long long N = a.N;
+  const bool wr = a.mask != nullptr && lane < TM / 32 && (long long)row0 + lane * 32 < N;
+#pragma unroll
+  for (int q = 0; q < SPW; ++q) {
+    const int sl = warp * SPW + q;
+    unsigned int mine = 0u;
+#pragma unroll
+    for (int g = 0; g < TM / 32; ++g) {
+      const int r = g * 32 + lane;
+      const int row = row0 + r;
+      const bool valid = row < N;
+      const float y = fmaf(sOut[sl * OUT_LD + r], a.ystd, a.c0);
+      const unsigned int word = __ballot_sync(0xffffffffu, valid && (y > a.tau));
+      st.cnt[q] += __popc(word);
+      if (lane == g) mine = word;
+      // rows only grow for a given lane, so a tie never replaces the earlier (smaller) index
+      if (valid && y > st.bv[q]) { st.bv[q] = y; st.bi[q] = row; }
+    }
+    if (wr && s0 + sl < a.lay.S) a.mask[(long long)(s0 + sl) * a.mask_ld + (row0 >> 5) + lane] = mine;
+  }
+}
+
+template <int NW>
+__device__ __forceinline__ void epilogue_levelset_reg_flush(const KArgs& a, LsRegState<NW>& st, int s0, int tid) {
+  constexpr int SPW = TN / NW;
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int q = 0; q < SPW; ++q) {
+    float bv = st.bv[q];
+    int bi = st.bi[q];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      const size_t o = (size_t)blockIdx.x * a.lay.Sp + s0 + warp * SPW + q;
+      a.p_cnt[o] = st.cnt[q];
+      a.p_max[o] = bv;
+      a.p_arg[o] = bi;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------
-template <int DP, int EPI>
+template <int DP, int EPI, bool BF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_constant__ KArgs a) {
-  extern __shared__ uint8_t smem_raw[];
+  using C = TcCfg<BF>;
+  // no-swizzle UMMA operands only need 16-byte alignment; plain array arithmetic keeps the
+  // shared address space visible to the compiler (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(128) uint8_t tc_smem[];
+  uint8_t* const smem = tc_smem;
   const Layout& lay = a.lay;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const TcSmem sl = tc_smem_layout(lay, EPI, a.k);
   uint8_t* sB = smem + sl.b;
   float* sFT = reinterpret_cast<float*>(smem + sl.ft);
@@ -220,19 +438,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   float* sState = reinterpret_cast<float*>(smem + sl.state);
   float* sIl = reinterpret_cast<float*>(smem + sl.il);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
-  uint64_t* b_full = bars;                 // [TC_NSB]
-  uint64_t* b_empty = bars + TC_NSB;       // [TC_NSB]
-  uint64_t* a_full = bars + 2 * TC_NSB;    // [2]
-  uint64_t* a_empty = a_full + 2;          // [2]
-  uint64_t* d_full = a_empty + 2;          // [2]
-  uint64_t* d_empty = d_full + 2;          // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(d_empty + 2);
+  uint64_t* b_full = bars;             // [8]
+  uint64_t* b_empty = bars + 8;        // [8]
+  uint64_t* a_full = bars + 16;        // [4]
+  uint64_t* a_empty = bars + 20;       // [4]
+  uint64_t* d_full = bars + 24;        // [2]
+  uint64_t* d_empty = bars + 26;       // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int nkb = lay.Kp / TK;
-  const int OS = lay.OS;
+  constexpr int OS = (DP + 1 + 3) / 4 * 4;  // == lay.OS for this DP (compile-time row stride)
   const int s0 = blockIdx.y * TN;
-  int t0, t1;
-  tc_tile_range(a.ntiles, gridDim.x, blockIdx.x, &t0, &t1);
+  const int npass = (a.ntiles + TC_TILES - 1) / TC_TILES;
+  int t0, t1;  // this CTA's contiguous range of passes (pairs of row tiles)
+  tc_tile_range(npass, gridDim.x, blockIdx.x, &t0, &t1);
   const EpiSmem e = epi_carve(sState, EPI, a.k);
 
   // ---- one-time setup ----
@@ -242,156 +461,275 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     for (int i = tid; i < round_up(lay.dp4, 4); i += TC_THREADS) sIl[i] = __ldg(a.pack + lay.off_invls + i);
   }
   if (tid == 0) {
-    for (int i = 0; i < TC_NSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], TC_NPROD);
-      mbar_init(&a_empty[i], 1);
-      mbar_init(&d_full[i], 1);
-      mbar_init(&d_empty[i], TC_NEPI);
-    }
+    for (int i = 0; i < C::NSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < C::NSA; ++i) { mbar_init(&a_full[i], TC_NPROD); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], TC_NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
+  if (warp == TC_WARP_ALLOC) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
                  "r"(TC_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= TC_EPI_WARP0) epi_init(e, EPI, a.k, tid - TC_EPI_WARP0 * 32, TC_NEPI * 32);
+  if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_NEPI) epi_init(e, EPI, a.k, tid - TC_EPI_WARP0 * 32, TC_NEPI * 32);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
 
-  if (warp == 0) {
+  if (warp == TC_WARP_LOAD) {
     // ================= B loader =================
-    if (lane == 0) {
-      const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.pack + lay.off_tc) +
-                          (size_t)blockIdx.y * nkb * TC_BBYTES;
-      uint32_t it = 0;
-      for (int tile = t0; tile < t1; ++tile) {
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t bs = it % TC_NSB, ph = (it / TC_NSB) & 1;
-          mbar_wait(&b_empty[bs], ph ^ 1);
-          mbar_arrive_expect_tx(&b_full[bs], TC_BBYTES);
-          bulk_g2s(sB + bs * TC_BBYTES, gB + (size_t)kb * TC_BBYTES, TC_BBYTES, &b_full[bs]);
+    const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.pack + lay.off_tc) +
+                        (size_t)blockIdx.y * nkb * C::BBYTES;
+    uint32_t it = 0;
+    for (int pass = t0; pass < t1; ++pass) {
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t bs = it % C::NSB, ph = (it / C::NSB) & 1;
+        if (lane == 0) mbar_wait(&b_empty[bs], ph ^ 1);
+        __syncwarp();
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&b_full[bs], C::BBYTES);
+          bulk_g2s(sB + bs * C::BBYTES, gB + (size_t)kb * C::BBYTES, C::BBYTES, &b_full[bs]);
         }
+        __syncwarp();
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == TC_WARP_MMA) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t IDESC_N128 = umma_idesc_tf32(128);
-      constexpr uint32_t IDESC_N64 = umma_idesc_tf32(64);
-      uint32_t it = 0, tl = 0;
-      for (int tile = t0; tile < t1; ++tile, ++tl) {
-        const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
-        mbar_wait(&d_empty[buf], dph ^ 1);
-        tc_fence_after();
-        const uint32_t d_addr = tmem + TC_COL_D + buf * 128;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t bs = it % TC_NSB, bph = (it / TC_NSB) & 1;
-          const uint32_t as = it & 1, aph = (it >> 1) & 1;
-          mbar_wait(&b_full[bs], bph);
-          mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          const uint32_t a_hi = tmem + TC_COL_A + as * 64, a_lo = a_hi + 32;
-          const uint32_t bbase = smem_u32(sB + bs * TC_BBYTES);
-#pragma unroll
-          for (int ks = 0; ks < TK / 8; ++ks) {
-            const uint64_t bd = umma_desc_kmajor(bbase + ks * 256, 128, 1024);
-            tc_mma_ts(d_addr, a_hi + ks * 8, bd, IDESC_N128, (kb | ks) ? 1u : 0u);
-            tc_mma_ts(d_addr, a_lo + ks * 8, bd, IDESC_N64, 1u);
+    // Lane 0 polls, the warp stays converged, one elected lane issues (straight UTC*MMA runs).
+    // tcgen05.mma issue blocks while the tensor pipe's short queue is full, so the readiness of
+    // the NEXT block is probed in the middle of the current one: its latency is then covered by
+    // queued MMAs instead of draining the pipe at the block boundary.
+    constexpr uint32_t IDESC = BF ? umma_idesc_bf16(TN) : umma_idesc_tf32(TN);
+    uint32_t it = 0, tl = 0;
+    bool ready = false;
+    for (int pass = t0; pass < t1; ++pass, ++tl) {
+      const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
+      mbar_wait_warp(&d_empty[buf], dph ^ 1, lane);
+      tc_fence_after();
+      const uint32_t d_addr = tmem + TC_COL_D + buf * (TC_TILES * TN);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t bs = it % C::NSB;
+        const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
+        TC_TRACE(0, it, 0);
+        if (!ready) {
+          if (lane == 0) {
+            mbar_wait(&b_full[bs], (it / C::NSB) & 1);
+            mbar_wait(&a_full[as], aph);
           }
-          tc_commit(&b_empty[bs]);
-          tc_commit(&a_empty[as]);
+          __syncwarp();
         }
-        tc_commit(&d_full[buf]);
+        TC_TRACE(0, it, 1);
+        tc_fence_after();
+        const uint32_t a_base = tmem + TC_COL_A + as * (TC_TILES * C::ACT);
+        const uint32_t bbase = smem_u32(sB + bs * C::BBYTES);
+#pragma unroll
+        for (int t = 0; t < TC_TILES; ++t) {
+          if (t == TC_TILES - 1) {  // probe block it + 1 while tile 0's MMAs are queued
+            const uint32_t nit = it + 1;
+            uint32_t ok = 0;
+            if (lane == 0)
+              ok = (mbar_test(&a_full[nit % C::NSA], (nit / C::NSA) & 1) &&
+                    mbar_test(&b_full[nit % C::NSB], (nit / C::NSB) & 1)) ? 1u : 0u;
+            ready = __shfl_sync(0xffffffffu, ok, 0) != 0;
+          }
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < C::KSTEPS; ++ks) {
+              const uint64_t b1 = umma_desc_kmajor(bbase + ks * C::B_KSTEP, 128, C::B_SBO);
+              const uint64_t b2 = umma_desc_kmajor(bbase + C::B_SPLIT2 + ks * C::B_KSTEP, 128, C::B_SBO);
+              const uint32_t a1 = a_base + t * C::ACT + ks * C::KCOLS, a2 = a1 + C::ACT / 2;
+              const uint32_t d = d_addr + t * TN;
+              if constexpr (BF) {
+                tc_mma_ts_bf16(d, a1, b1, IDESC, (kb | ks) ? 1u : 0u);
+                tc_mma_ts_bf16(d, a1, b2, IDESC, 1u);
+                tc_mma_ts_bf16(d, a2, b1, IDESC, 1u);
+              } else {
+                tc_mma_ts(d, a1, b1, IDESC, (kb | ks) ? 1u : 0u);
+                tc_mma_ts(d, a1, b2, IDESC, 1u);
+                tc_mma_ts(d, a2, b1, IDESC, 1u);
+              }
+            }
+            if (t == TC_TILES - 1) {  // release the stages (and publish the accumulators)
+              tc_commit(&b_empty[bs]);
+              tc_commit(&a_empty[as]);
+              if (kb == nkb - 1) tc_commit(&d_full[buf]);
+            }
+          }
+          __syncwarp();
+        }
+        TC_TRACE(0, it, 2);
       }
     }
   } else if (warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_NPROD) {
     // ================= producers =================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int h = (warp - TC_PROD_WARP0) >> 2;    // which 16 of the block's 32 features
+    const int h = (warp - TC_PROD_WARP0) >> 2;    // which 8 of the block's 32 features
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const bool tracer = (warp == TC_PROD_WARP0 && lane == 0);
+    (void)tracer;
     uint32_t it = 0;
-    for (int tile = t0; tile < t1; ++tile) {
-      const long long row = (long long)tile * TM + q * 32 + lane;
-      float x[DP], xs[DP];
+    for (int pass = t0; pass < t1; ++pass) {
+      float x[TC_TILES][DP];
 #pragma unroll
-      for (int i = 0; i < DP; ++i) {
-        x[i] = (row < a.N && i < lay.d) ? __ldg(a.X + row * lay.d + i) : 0.f;
-        xs[i] = x[i] * sIl[i];
+      for (int t = 0; t < TC_TILES; ++t) {
+        const long long row = ((long long)pass * TC_TILES + t) * TM + q * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < DP; ++i) x[t][i] = (row < a.N && i < lay.d) ? __ldg(a.X + row * lay.d + i) : 0.f;
       }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const uint32_t as = it & 1, aph = (it >> 1) & 1;
-        uint32_t hi[16], lo[16];
-        const int kbase = kb * TK + h * 16;
+        const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
+        const int kbase0 = kb * TK + h * TC_FPW;
+        if (tracer) TC_TRACE(1, it, 0);
+        bool free_now = true;
+        if (lane == 0) free_now = mbar_test(&a_empty[as], aph ^ 1);  // latency hidden behind the math
+        constexpr int NG = TC_FPW / 8;
+        uint32_t s1[NG][TC_TILES][C::WCOLS], s2[NG][TC_TILES][C::WCOLS];
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const bool rff = (kbase + g * 8) < lay.Lp_ft;  // warp-uniform, sections are multiples of 8
+        for (int g = 0; g < NG; ++g) {
+          // 8 features for both tiles' rows: each table row is fetched once and used twice.
+          // The RFF / kernel-feature branch is warp-uniform (sections are multiples of 8).
+          const int kbase = kbase0 + g * 8;
+          const float* ft = sFT + kbase * OS;
+          float v[TC_TILES][8];
+          if (kbase < lay.Lp_ft) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float* ft = sFT + (kbase + g * 8 + j) * OS;
-            float v;
-            if (rff) v = __cosf(rff_arg<DP>(ft, x));
-            else v = kernel_profile(kern_r2<DP>(ft, xs), lay.kernel);
-            const uint32_t hb = __float_as_uint(v) & 0xffffe000u;
-            hi[g * 8 + j] = hb;
-            lo[g * 8 + j] = __float_as_uint(v - __uint_as_float(hb));
+            for (int j = 0; j < 8; ++j) {
+              float w[OS];
+              load_row<OS>(ft + j * OS, w);
+#pragma unroll
+              for (int t = 0; t < TC_TILES; ++t) {
+                float arg = w[DP];
+#pragma unroll
+                for (int i = 0; i < DP; ++i) arg = fmaf(x[t][i], w[i], arg);
+                v[t][j] = __cosf(arg);
+              }
+            }
+          } else {
+            float r2[TC_TILES][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float w[OS];
+              load_row<OS>(ft + j * OS, w);
+#pragma unroll
+              for (int t = 0; t < TC_TILES; ++t) {
+                float acc = 0.f;
+#pragma unroll
+                for (int i = 0; i < DP; ++i) {
+                  const float df = fmaf(x[t][i], sIl[i], w[i]);
+                  acc = fmaf(df, df, acc);
+                }
+                r2[t][j] = acc;
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < TC_TILES; ++t) kernel_profile8(r2[t], v[t], lay.kernel);
+          }
+          // split into the two MMA operands
+#pragma unroll
+          for (int t = 0; t < TC_TILES; ++t) {
+            if constexpr (BF) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {  // column c packs features 2c (low half) and 2c + 1 (high half)
+                const uint32_t p1 = cvt_bf16x2(v[t][2 * c + 1], v[t][2 * c]);
+                const float r0 = v[t][2 * c] - __uint_as_float(p1 << 16);
+                const float r1 = v[t][2 * c + 1] - __uint_as_float(p1 & 0xffff0000u);
+                s1[g][t][c] = p1;
+                s2[g][t][c] = cvt_bf16x2(r1, r0);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t hb = __float_as_uint(v[t][j]) & 0xffffe000u;
+                s1[g][t][j] = hb;
+                s2[g][t][j] = __float_as_uint(v[t][j] - __uint_as_float(hb));
+              }
+            }
           }
         }
-        mbar_wait(&a_empty[as], aph ^ 1);
+        if (tracer) TC_TRACE(1, it, 1);
+        if (!free_now) mbar_wait(&a_empty[as], aph ^ 1);  // only lane 0 can have free_now == false
+        __syncwarp();
+        if (tracer) TC_TRACE(1, it, 2);
         tc_fence_after();
-        const uint32_t col = TC_COL_A + as * 64 + h * 16;
-        tc_st16(lane_addr + col, hi);
-        tc_st16(lane_addr + col + 32, lo);
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+          for (int t = 0; t < TC_TILES; ++t) {
+            const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + (h * NG + g) * C::WCOLS;
+            if constexpr (BF) {
+              tc_st4(lane_addr + col, s1[g][t]);
+              tc_st4(lane_addr + col + C::ACT / 2, s2[g][t]);
+            } else {
+              tc_st8(lane_addr + col, s1[g][t]);
+              tc_st8(lane_addr + col + C::ACT / 2, s2[g][t]);
+            }
+          }
         tc_wait_st();
+        if (tracer) TC_TRACE(1, it, 3);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[as]);
+        if (tracer) TC_TRACE(1, it, 4);
       }
     }
-  } else if (warp >= TC_EPI_WARP0) {
+  } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_NEPI) {
     // ================= epilogue =================
     const int q = warp & 3;
     const int etid = tid - TC_EPI_WARP0 * 32;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    LsRegState<TC_NEPI> ls;
+    ls.init();
     uint32_t tl = 0;
-    for (int tile = t0; tile < t1; ++tile, ++tl) {
+    for (int pass = t0; pass < t1; ++pass, ++tl) {
       const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
-      mbar_wait(&d_full[buf], dph);
+      if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 0);
+      mbar_wait_warp(&d_full[buf], dph, lane);
+      if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 1);
       tc_fence_after();
       const int r = q * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < TN / 16; ++c) {
-        uint32_t u[16], w[16];
-        tc_ld16(lane_addr + TC_COL_D + buf * 128 + c * 16, u);
-        tc_ld16(lane_addr + TC_COL_D + buf * 128 + 64 + c * 16, w);
-        tc_wait_ld();
+      for (int t = 0; t < TC_TILES; ++t) {
+        const int tile = pass * TC_TILES + t;
+        if (tile < a.ntiles) {
+#pragma unroll 1
+          for (int c = 0; c < TN / 16; ++c) {
+            uint32_t u[16];
+            tc_ld16(lane_addr + TC_COL_D + (buf * TC_TILES + t) * TN + c * 16, u);
+            tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          sOut[(c * 16 + j) * OUT_LD + r] = __uint_as_float(u[j]) + __uint_as_float(w[j]);
+            for (int j = 0; j < 16; ++j) sOut[(c * 16 + j) * OUT_LD + r] = __uint_as_float(u[j]);
+          }
+        }
+        if (t == TC_TILES - 1) {  // both tiles' accumulators have left tensor memory: release D[buf]
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d_empty[buf]);
+          if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 2);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
+        if (tile < a.ntiles) {
+          if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg<TC_NEPI>(a, sOut, ls, tile * TM, s0, etid);
+          else epilogue_tile<EPI, TC_NEPI>(a, sOut, e, tile * TM, s0, etid);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&d_empty[buf]);
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
-      epilogue_tile<EPI, TC_NEPI>(a, sOut, e, tile * TM, s0, etid);
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
+      if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 3);
     }
-    epilogue_flush<EPI>(a, e, s0, etid, TC_NEPI * 32);
+    if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg_flush<TC_NEPI>(a, ls, s0, etid);
+    else epilogue_flush<EPI>(a, e, s0, etid, TC_NEPI * 32);
   }
 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == TC_WARP_ALLOC) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
   }
 }
 
-template <int EPI>
+template <int EPI, bool BF>
 int tensor_launch_epi(const KArgs& a0, int sms, cudaStream_t st, char* err, size_t errlen) {
   KArgs a = a0;
   const Layout& l = a.lay;
@@ -402,11 +740,11 @@ int tensor_launch_epi(const KArgs& a0, int sms, cudaStream_t st, char* err, size
     return PSBAX_E_UNSUPPORTED;
   }
   cudaError_t ce = cudaSuccess;
-#define TC_LAUNCH(DPV)                                                                              \
-  do {                                                                                              \
-    ce = cudaFuncSetAttribute(k_shared_tensor<DPV, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                              (int)sl.total);                                                       \
-    if (ce == cudaSuccess) k_shared_tensor<DPV, EPI><<<dim3(gx, gy), TC_THREADS, sl.total, st>>>(a);  \
+#define TC_LAUNCH(DPV)                                                                                  \
+  do {                                                                                                  \
+    ce = cudaFuncSetAttribute(k_shared_tensor<DPV, EPI, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                              (int)sl.total);                                                           \
+    if (ce == cudaSuccess) k_shared_tensor<DPV, EPI, BF><<<dim3(gx, gy), TC_THREADS, sl.total, st>>>(a);  \
   } while (0)
   switch (l.dp4) {
     case 2: TC_LAUNCH(2); break;
@@ -428,9 +766,14 @@ int tensor_launch_epi(const KArgs& a0, int sms, cudaStream_t st, char* err, size
 }
 
 inline int tensor_launch(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
-  if (epi == EPI_VALUES) return tensor_launch_epi<EPI_VALUES>(a, sms, st, err, errlen);
-  if (epi == EPI_LEVELSET) return tensor_launch_epi<EPI_LEVELSET>(a, sms, st, err, errlen);
-  return tensor_launch_epi<EPI_TOPK>(a, sms, st, err, errlen);
+  if (a.lay.mode == MODE_TENSOR_BF16) {
+    if (epi == EPI_VALUES) return tensor_launch_epi<EPI_VALUES, true>(a, sms, st, err, errlen);
+    if (epi == EPI_LEVELSET) return tensor_launch_epi<EPI_LEVELSET, true>(a, sms, st, err, errlen);
+    return tensor_launch_epi<EPI_TOPK, true>(a, sms, st, err, errlen);
+  }
+  if (epi == EPI_VALUES) return tensor_launch_epi<EPI_VALUES, false>(a, sms, st, err, errlen);
+  if (epi == EPI_LEVELSET) return tensor_launch_epi<EPI_LEVELSET, false>(a, sms, st, err, errlen);
+  return tensor_launch_epi<EPI_TOPK, false>(a, sms, st, err, errlen);
 }
 
 }  // namespace psbax

@@ -46,7 +46,8 @@ def _tensor_ok(c):
     return G == 1 and S >= 16 and L > 0 and d <= 16
 
 
-ENGINE_CASES = [(c, "simt") for c in CASES] + [(c, "tensor") for c in CASES if _tensor_ok(c)]
+ENGINE_CASES = ([(c, "simt") for c in CASES] + [(c, "tensor") for c in CASES if _tensor_ok(c)] +
+                [(c, "tensor_bf16") for c in CASES if _tensor_ok(c)])
 _REF_CACHE = {}
 
 
@@ -134,7 +135,7 @@ def test_topk(case, k):
         assert set(sure.tolist()) <= set(idx[s].tolist())
 
 
-@pytest.mark.parametrize("engine", ["simt", "tensor"])
+@pytest.mark.parametrize("engine", ["simt", "tensor", "tensor_bf16"])
 def test_ties_break_towards_smaller_index(engine):
     p = random_params(16, 64, 2, 8, seed=3)
     base = candidates(50, 2)
@@ -150,7 +151,7 @@ def test_ties_break_towards_smaller_index(engine):
     assert (am.cpu().numpy() == idx[:, 0]).all()
 
 
-@pytest.mark.parametrize("engine", ["simt", "tensor"])
+@pytest.mark.parametrize("engine", ["simt", "tensor", "tensor_bf16"])
 def test_row_offset_and_sharded_merge_equal_whole(engine):
     """Shards of the candidate set + psbax_topk_merge == one launch over the whole set, bit for bit."""
     import ctypes as C
@@ -255,13 +256,14 @@ def test_errors_are_reported():
         batch.values(candidates(10, 3).cuda())
 
 
-def test_tensor_engine_many_tiles_matches_simt():
+@pytest.mark.parametrize("engine", ["tensor", "tensor_bf16"])
+def test_tensor_engine_many_tiles_matches_simt(engine):
     """Several tiles per persistent CTA (accumulator double-buffering, barrier phase wrap-around)
-    and several sample chunks: the tcgen05 engine against the FFMA engine and the oracle."""
+    and several sample chunks: the tcgen05 engines against the FFMA engine and the oracle."""
     p = random_params(100, 1000, 2, 64, seed=21)
     N = 148 * 128 * 5 + 77
     X = candidates(N, 2).cuda()
-    bt, bs = to_batch(p, engine="tensor"), to_batch(p, engine="simt")
+    bt, bs = to_batch(p, engine=engine), to_batch(p, engine="simt")
     vt, vs = bt.values(X), bs.values(X)
     tol = torch.from_numpy(_tol(p)).cuda().float()
     assert ((vt - vs).abs().max(0).values <= tol).all()
@@ -277,5 +279,8 @@ def test_tensor_engine_many_tiles_matches_simt():
     tv, ti = bt.topk(X, 10)
     sv, si = bs.topk(X, 10)
     assert ((tv - sv).abs() <= tol[:, None]).all()
-    same = (ti == si).all(1).cpu().numpy()
-    assert same.mean() > 0.9  # near-ties between the engines may swap neighbours
+    # index sets identical wherever the gap between the 10th and 11th value exceeds tolerance
+    top11 = torch.topk(vs, 11, dim=0).values  # [11, S]
+    clear = (top11[9] - top11[10]) > 2 * tol
+    same_set = torch.tensor([set(ti[s].tolist()) == set(si[s].tolist()) for s in range(ti.shape[0])]).cuda()
+    assert (same_set | ~clear).all()
