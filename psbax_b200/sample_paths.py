@@ -161,6 +161,78 @@ class SamplePathBatch:
                 argmax.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()), "psbax_eval_levelset")
         return LevelSetResult(mask, count, maxval, argmax, N)
 
+    def levelset_streamed(self, X_host: torch.Tensor, threshold: float, chunk_rows: int = 1 << 21,
+                          row_offset: int = 0):
+        """Level set of a HOST-resident candidate set, pipelined: the rows are cut into chunks and
+        chunk i+1 is uploaded (copy stream) while chunk i is evaluated (compute stream) and the
+        mask of chunk i-1 is downloaded (second copy stream).  ``X_host`` should be pinned float32.
+
+        Returns (mask_chunks, bounds, count, maxval, argmax): ``mask_chunks[c]`` is a pinned int32
+        [S, ceil(rows_c / 32)] tensor for rows [bounds[c], bounds[c+1]); count / maxval / argmax
+        are host tensors over the whole set.  The staging buffers (device double buffer, pinned
+        result buffers) are cached per (N, chunk_rows) and reused: the returned tensors stay valid
+        until the next call with the same shape."""
+        X_host = torch.as_tensor(X_host)
+        if X_host.device.type != "cpu" or X_host.dtype != F32 or X_host.dim() != 2 or X_host.shape[1] != self.d:
+            raise PsbaxError("levelset_streamed expects a CPU float32 [N, d] tensor")
+        N = X_host.shape[0]
+        chunk_rows = max(4096, (chunk_rows // 256) * 256)
+        bounds = list(range(0, N, chunk_rows)) + [N]
+        nchunk = len(bounds) - 1
+        dev = self.device
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, "_streams", None) is None:
+                self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            s_in, s_out = self._streams
+            cache = getattr(self, "_stream_cache", None)
+            if cache is None or cache[0] != (N, chunk_rows):
+                xbuf = [torch.empty(chunk_rows, self.d, dtype=F32, device=dev) for _ in range(2)]
+                masks_h = [torch.empty(self.S, (bounds[c + 1] - bounds[c] + 31) // 32, dtype=torch.int32).pin_memory()
+                           for c in range(nchunk)]
+                small = (torch.empty(self.S, dtype=torch.int64).pin_memory(),
+                         torch.empty(self.S, dtype=F32).pin_memory(),
+                         torch.empty(self.S, dtype=torch.int64).pin_memory())
+                self._stream_cache = ((N, chunk_rows), xbuf, masks_h, small)
+            _, xbuf, masks_h, (cnt_h, bv_h, bi_h) = self._stream_cache
+            ev_in = [torch.cuda.Event() for _ in range(nchunk)]
+            ev_done = [torch.cuda.Event() for _ in range(nchunk)]
+            ev_free = [None, None]  # compute finished with xbuf[b]
+            s_in.wait_stream(main)
+            s_out.wait_stream(main)
+            tot = torch.zeros(self.S, dtype=torch.int64, device=dev)
+            best_v = torch.full((self.S,), float("-inf"), dtype=F32, device=dev)
+            best_i = torch.full((self.S,), -1, dtype=torch.int64, device=dev)
+            results = []
+            for c in range(nchunk):
+                lo, hi = bounds[c], bounds[c + 1]
+                b = c & 1
+                with torch.cuda.stream(s_in):
+                    if ev_free[b] is not None:
+                        s_in.wait_event(ev_free[b])
+                    xbuf[b][: hi - lo].copy_(X_host[lo:hi], non_blocking=True)
+                    ev_in[c].record(s_in)
+                main.wait_event(ev_in[c])
+                r = self.levelset(xbuf[b][: hi - lo], threshold, True, row_offset + lo)
+                ev_free[b] = torch.cuda.Event()
+                ev_free[b].record(main)
+                tot += r.count
+                upd = r.maxval > best_v
+                best_v = torch.where(upd, r.maxval, best_v)
+                best_i = torch.where(upd, r.argmax, best_i)
+                ev_done[c].record(main)
+                results.append(r)  # keeps the device mask alive until its download is queued
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[c])
+                    masks_h[c].copy_(r.mask, non_blocking=True)
+                    r.mask.record_stream(s_out)
+            cnt_h.copy_(tot, non_blocking=True)
+            bv_h.copy_(best_v, non_blocking=True)
+            bi_h.copy_(best_i, non_blocking=True)
+            main.wait_stream(s_out)
+            main.synchronize()
+        return masks_h, bounds, cnt_h, bv_h, bi_h
+
     def argmax(self, X, row_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
         """Per-sample max and arg max over the candidates (ES-population scoring)."""
         r = self.levelset(X, float("inf"), want_mask=False, row_offset=row_offset)

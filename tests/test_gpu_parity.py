@@ -284,3 +284,19 @@ def test_tensor_engine_many_tiles_matches_simt(engine):
     clear = (top11[9] - top11[10]) > 2 * tol
     same_set = torch.tensor([set(ti[s].tolist()) == set(si[s].tolist()) for s in range(ti.shape[0])]).cuda()
     assert (same_set | ~clear).all()
+
+
+def test_levelset_streamed_equals_resident():
+    """Host-resident candidates streamed in chunks == one launch over the resident set."""
+    p = random_params(64, 200, 2, 16, seed=31)
+    batch = to_batch(p)
+    X = candidates(50_000, 2)
+    tau = 0.3
+    whole = batch.levelset(X.cuda(), tau)
+    masks, bounds, cnt, bv, bi = batch.levelset_streamed(X.pin_memory(), tau, chunk_rows=8192)
+    assert bounds[0] == 0 and bounds[-1] == 50_000 and len(masks) == len(bounds) - 1
+    ref_mask = unpack_mask(whole.mask, 50_000)
+    got = np.concatenate([unpack_mask(m, bounds[c + 1] - bounds[c]) for c, m in enumerate(masks)], axis=1)
+    assert (got == ref_mask).all()
+    assert torch.equal(cnt, whole.count.cpu()) and torch.equal(bv, whole.maxval.cpu())
+    assert torch.equal(bi, whole.argmax.cpu())
