@@ -357,19 +357,22 @@ int psbax_subset_select(const float* fx, int64_t ld_fx, const float* etas, int64
   int rc = device_sms(&sms);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int T = (S >= 4 * sms) ? 8 : (S >= 2 * sms) ? 4 : 1;
-  const size_t smem = (size_t)T * B * 4 + (size_t)T * k * 4 + (size_t)T * 8 * 8;
+  // T samples per CTA share every eta load; keep >= ~2 CTAs of 512 threads per SM in flight
+  const int T = (S >= 16 * sms) ? 8 : (S >= 4 * sms) ? 4 : (S >= 2 * sms) ? 2 : 1;
+  const int threads = (N >= 4096) ? 512 : 256;
+  const size_t smem = (size_t)T * B * 4 + (size_t)T * k * 4 + (size_t)T * 32 * 8;
   if (smem > 200 * 1024) return fail(PSBAX_E_UNSUPPORTED, "B=%d too large for shared memory", B);
   const int grid = (S + T - 1) / T;
 #define LAUNCH_SS(TT)                                                                           \
   do {                                                                                          \
     if (smem > 48 * 1024)                                                                       \
       CUDA_TRY(cudaFuncSetAttribute(k_subset_select<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_subset_select<TT><<<grid, 256, smem, st>>>(fx, ld_fx, etas, N, B, S, k, nonneg,          \
+    k_subset_select<TT><<<grid, threads, smem, st>>>(fx, ld_fx, etas, N, B, S, k, nonneg,          \
                                                  reinterpret_cast<long long*>(out_idx));        \
   } while (0)
   if (T == 8) LAUNCH_SS(8);
   else if (T == 4) LAUNCH_SS(4);
+  else if (T == 2) LAUNCH_SS(2);
   else LAUNCH_SS(1);
 #undef LAUNCH_SS
   CUDA_TRY(cudaGetLastError());

@@ -12,7 +12,7 @@ namespace psbax {
 //   pick t >= 1 = arg max_j mean_b max(cur[b], values[b, j]), chosen j score 0
 // ---------------------------------------------------------------------------------
 template <int T>
-__global__ void __launch_bounds__(256) k_subset_select(const float* __restrict__ fx,
+__global__ void __launch_bounds__(1024) k_subset_select(const float* __restrict__ fx,
                                                        long long ld_fx,
                                                        const float* __restrict__ etas,
                                                        long long N, int B, int S, int k,
@@ -20,8 +20,8 @@ __global__ void __launch_bounds__(256) k_subset_select(const float* __restrict__
   extern __shared__ __align__(16) float smem[];
   float* cur = smem;                                   // [T][B]
   int* chosen = reinterpret_cast<int*>(cur + T * B);   // [T][k]
-  float* redv = reinterpret_cast<float*>(chosen + T * k);  // [T][8]
-  int* redi = reinterpret_cast<int*>(redv + T * 8);        // [T][8]
+  float* redv = reinterpret_cast<float*>(chosen + T * k);  // [T][32]
+  int* redi = reinterpret_cast<int*>(redv + T * 32);       // [T][32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sbase = blockIdx.x * T;
   const float invB = 1.0f / (float)B;
@@ -68,14 +68,14 @@ __global__ void __launch_bounds__(256) k_subset_select(const float* __restrict__
         const int oi = __shfl_xor_sync(0xffffffffu, bi[t], off);
         if (better(ov, oi, bv[t], bi[t])) { bv[t] = ov; bi[t] = oi; }
       }
-      if (lane == 0) { redv[t * 8 + warp] = bv[t]; redi[t * 8 + warp] = bi[t]; }
+      if (lane == 0) { redv[t * 32 + warp] = bv[t]; redi[t * 32 + warp] = bi[t]; }
     }
     __syncthreads();
     if (tid < T) {
-      float v = redv[tid * 8];
-      int i = redi[tid * 8];
+      float v = redv[tid * 32];
+      int i = redi[tid * 32];
       for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-        if (better(redv[tid * 8 + w], redi[tid * 8 + w], v, i)) { v = redv[tid * 8 + w]; i = redi[tid * 8 + w]; }
+        if (better(redv[tid * 32 + w], redi[tid * 32 + w], v, i)) { v = redv[tid * 32 + w]; i = redi[tid * 32 + w]; }
       chosen[tid * k + step] = i;
       if (sbase + tid < S) out_idx[(long long)(sbase + tid) * k + step] = i;
     }
