@@ -305,7 +305,11 @@ def run_ours(args):
                     "ms_per_step": 1e3 * t_e2e_max / K},
             "gpu_launches": 2 * K,  # per step: fused evaluate+level-set kernel + finalize (device-resident loop)
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": None,
+                         "frac": achieved / peak_tf,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, one
+                         # ncu --set full capture (profiles/r01_ncu_bench_kernel_bf16x3_details.csv);
+                         # algorithmic bytes = 134.2 MB X* + 134.2 MB mask
+                         "traffic": 226.6e6 if eng == "tensor_bf16x3" else None,
                          "kernel": "fused evaluate+level-set kernel (+3 us finalize)",
                          "kernel_ms": 1e3 * kern_s,
                          "note": (f"algorithmic flops = 2*(L+n)*S per candidate = {2 * (L + NTRAIN) * S}; "

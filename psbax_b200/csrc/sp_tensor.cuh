@@ -161,6 +161,15 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// relaxed wait for roles with slack (producers on a 4-stage ring): a failed probe sleeps a few
+// tens of ns instead of re-polling at full rate (polls were ~15 % of all issued instructions)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(32);
+    if (++spins > (1u << 24)) asm volatile("trap;");
+  }
+}
 // one lane polls, the warp follows: 32 lanes hitting the same mbarrier word serialise in the
 // shared-memory sync unit (measured: a dominant per-block cost with 16 producer warps)
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
@@ -582,8 +591,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
         const int kbase0 = kb * TK + h * TC_FPW;
         if (tracer) TC_TRACE(1, it, 0);
-        bool free_now = true;
-        if (lane == 0) free_now = mbar_test(&a_empty[as], aph ^ 1);  // latency hidden behind the math
         constexpr int NG = TC_FPW / 8;
         uint32_t s1[NG][TC_TILES][C::WCOLS], s2[NG][TC_TILES][C::WCOLS];
 #pragma unroll
@@ -649,7 +656,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           }
         }
         if (tracer) TC_TRACE(1, it, 1);
-        if (!free_now) mbar_wait(&a_empty[as], aph ^ 1);  // only lane 0 can have free_now == false
+        if (lane == 0) {
+          if constexpr (BF) mbar_wait_relaxed(&a_empty[as], aph ^ 1);
+          else mbar_wait(&a_empty[as], aph ^ 1);
+        }
         __syncwarp();
         if (tracer) TC_TRACE(1, it, 2);
         tc_fence_after();
