@@ -300,3 +300,46 @@ def test_levelset_streamed_equals_resident():
     assert (got == ref_mask).all()
     assert torch.equal(cnt, whole.count.cpu()) and torch.equal(bv, whole.maxval.cpu())
     assert torch.equal(bi, whole.argmax.cpu())
+
+
+def test_randomised_shapes_all_engines():
+    """Seeded sweep over random shapes (dims, feature counts, sample counts, ragged N, both basis
+    modes, every kernel): values / level set / top-k of every engine that supports the shape against
+    the oracle."""
+    rng = np.random.default_rng(2024)
+    kernels = ["rbf", "matern12", "matern32", "matern52"]
+    for trial in range(24):
+        d = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 33]))
+        L = int(rng.choice([0, 8, 37, 100, 256, 1000]))
+        n = int(rng.choice([0, 1, 5, 64, 130]))
+        if L + n == 0:
+            n = 3
+        S = int(rng.choice([1, 2, 3, 15, 16, 17, 63, 64, 65, 130]))
+        G = 1 if (L == 0 or rng.random() < 0.6) else S
+        N = int(rng.choice([1, 31, 32, 33, 127, 128, 129, 255, 257, 1000, 4097]))
+        kernel = kernels[trial % 4]
+        p = random_params(S, L, d, n, G=G, kernel=kernel, seed=100 + trial)
+        X = candidates(N, d, seed=trial)
+        ref = O.eval_paths(p, X.double()).numpy()
+        tol = _tol(p)
+        engines = ["simt"]
+        if G == 1 and S >= 16 and L > 0 and d <= 16:
+            engines += ["tensor", "tensor_bf16"]
+        for eng in engines:
+            b = to_batch(p, engine=eng)
+            tag = (trial, eng, S, L, d, n, G, kernel, N)
+            out = b.values(X.cuda()).double().cpu().numpy()
+            assert (np.abs(out - ref).max(axis=0) <= tol).all(), tag
+            tau = float(np.median(ref))
+            res = b.levelset(X.cuda(), tau)
+            mask = unpack_mask(res.mask, N)
+            decided = (np.abs(ref - tau) > tol[None, :]).T
+            assert (mask[decided] == (ref > tau).T[decided]).all(), tag
+            assert (res.count.cpu().numpy() == mask.sum(1)).all(), tag
+            assert (np.abs(res.maxval.double().cpu().numpy() - ref.max(0)) <= tol).all(), tag
+            k = min(N, int(rng.choice([1, 2, 10, 33, 64])))
+            val, idx = b.topk(X.cuda(), k)
+            val, idx = val.double().cpu().numpy(), idx.cpu().numpy()
+            srt = -np.sort(-ref, axis=0)[:k].T  # [S, k]
+            assert (np.abs(val - srt) <= tol[:, None]).all(), tag
+            assert (np.abs(np.take_along_axis(ref.T, idx, 1) - val) <= tol[:, None]).all(), tag
