@@ -335,9 +335,7 @@ def paths_engine(paths):
         return "simt"
     if paths.engine == "tensor":
         return "tensor_tf32x3"
-    if paths.engine == "tensor_bf16" or paths.d <= 16:
-        return "tensor_bf16x3"
-    return "simt"
+    return "tensor_bf16x3"
 
 
 def main():

@@ -56,10 +56,11 @@ int validate(const psbax_paths_t* p) {
     return fail(PSBAX_E_INVALID, "Xtrain / inv_ls / V must be non-NULL when n > 0");
   if (p->engine < PSBAX_ENGINE_AUTO || p->engine > PSBAX_ENGINE_TENSOR_BF16)
     return fail(PSBAX_E_INVALID, "unknown engine id %d", p->engine);
-  if ((p->engine == PSBAX_ENGINE_TENSOR || p->engine == PSBAX_ENGINE_TENSOR_BF16) && !tensor_supported(p))
+  if ((p->engine == PSBAX_ENGINE_TENSOR && !tensor_supported(p, false)) ||
+      (p->engine == PSBAX_ENGINE_TENSOR_BF16 && !tensor_supported(p, true)))
     return fail(PSBAX_E_UNSUPPORTED,
-                "tensor engine needs a shared basis (G == 1), d <= %d and S <= %d (got G=%d d=%d S=%d)",
-                TC_MAX_D, TC_MAX_S, p->G, p->d, p->S);
+                "tensor engine needs a shared basis (G == 1), S >= 16, L > 0, d <= %d and operands that fit "
+                "shared memory (got G=%d d=%d S=%d L=%d n=%d)", TC_MAX_D, p->G, p->d, p->S, p->L, p->n);
   return PSBAX_OK;
 }
 
@@ -75,7 +76,7 @@ Layout make_layout(const psbax_paths_t* p) {
   const bool shared = (p->G == 1) && (p->S >= 16) && (p->L > 0);
   if (!shared) l.mode = MODE_PERSAMPLE;
   else if (p->engine == PSBAX_ENGINE_TENSOR) l.mode = MODE_TENSOR;
-  else if (p->engine == PSBAX_ENGINE_TENSOR_BF16 || (p->engine == PSBAX_ENGINE_AUTO && tensor_supported(p)))
+  else if (p->engine == PSBAX_ENGINE_TENSOR_BF16 || (p->engine == PSBAX_ENGINE_AUTO && tensor_supported(p, true)))
     l.mode = MODE_TENSOR_BF16;  // AUTO: the faster split; both hold the 1e-4 contract
   else l.mode = MODE_SHARED_SIMT;
   l.Lp_ft = (l.mode == MODE_PERSAMPLE) ? 0 : l.Lp;

@@ -37,7 +37,9 @@
 
 namespace psbax {
 
-constexpr int TC_MAX_D = 16;
+constexpr int TC_MAX_D = 128;           // d <= 16: x in registers; larger d: x tile in shared memory
+constexpr int TC_MAX_D_REG = 16;
+constexpr int TC_NSB_GENERIC = 4;       // B + feature-table ring depth of the generic-d kernels
 constexpr int TC_MAX_S = 1 << 20;  // any S: processed in chunks of 64 samples
 #ifndef PSBAX_TC_NPROD
 #define PSBAX_TC_NPROD 16
@@ -82,9 +84,7 @@ constexpr int TC_COL_D = 0, TC_COL_A = 256;
 constexpr int TC_TILES = 2;                  // row tiles per CTA pass
 constexpr uint32_t TC_TMEM_COLS = 512;
 
-inline bool tensor_supported(const psbax_paths_t* p) {
-  return p->G == 1 && p->S >= 16 && p->L > 0 && p->d <= TC_MAX_D;
-}
+inline bool tensor_supported(const psbax_paths_t* p, bool bf16);
 inline bool is_tensor_mode(int mode) { return mode == MODE_TENSOR || mode == MODE_TENSOR_BF16; }
 // [chunks][nkb] images of BBYTES
 inline size_t tensor_pack_floats(const Layout& l) {
@@ -277,14 +277,22 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int N) {
 #endif
 
 struct TcSmem {
-  uint32_t b, ft, out, state, il, bars, total;  // byte offsets into dynamic shared memory
+  // byte offsets into dynamic shared memory.  `b`: ring of NSB stages of `stage` bytes: the B
+  // image and, for generic d, the 32-row block of the feature table behind it.
+  uint32_t b, stage, nsb, ft, x, out, state, il, bars, total;
+  bool generic;
 };
-__host__ __device__ inline TcSmem tc_smem_layout(const Layout& l, int epi, int k) {
+__host__ __device__ inline TcSmem tc_smem_layout_impl(const Layout& l, int epi, int k, bool generic) {
   const bool bf = l.mode == MODE_TENSOR_BF16;
   TcSmem s{};
+  s.generic = generic;
+  const uint32_t bbytes = bf ? TcCfg<true>::BBYTES : TcCfg<false>::BBYTES;
+  s.nsb = s.generic ? TC_NSB_GENERIC : (bf ? TcCfg<true>::NSB : TcCfg<false>::NSB);
+  s.stage = bbytes + (s.generic ? (uint32_t)TK * l.OS * 4 : 0u);
   uint32_t o = 0;
-  s.b = o;     o += bf ? TcCfg<true>::NSB * TcCfg<true>::BBYTES : TcCfg<false>::NSB * TcCfg<false>::BBYTES;
-  s.ft = o;    o += (uint32_t)l.Kp * l.OS * 4;
+  s.b = o;     o += s.nsb * s.stage;
+  s.ft = o;    o += s.generic ? 0u : (uint32_t)l.Kp * l.OS * 4;             // resident table (small d)
+  s.x = o;     o += s.generic ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u;   // x tile [tile][i][row]
   s.out = o;   o += TN * OUT_LD * 4;
   s.state = o; o += (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;
   s.il = o;    o += (uint32_t)round_up(l.dp4, 4) * 4;
@@ -293,12 +301,32 @@ __host__ __device__ inline TcSmem tc_smem_layout(const Layout& l, int epi, int k
   s.total = o;
   return s;
 }
+constexpr uint32_t TC_SMEM_MAX = 227 * 1024;
+// resident feature table when it fits (d <= 16), else the generic kernel with streamed table blocks
+__host__ __device__ inline TcSmem tc_smem_layout(const Layout& l, int epi, int k) {
+  if (l.dp4 <= TC_MAX_D_REG) {
+    const TcSmem r = tc_smem_layout_impl(l, epi, k, false);
+    if (r.total <= TC_SMEM_MAX) return r;
+  }
+  return tc_smem_layout_impl(l, epi, k, true);
+}
 
 // CTA c of gx handles the contiguous range [t0, t1) of passes
 __host__ __device__ inline void tc_tile_range(int n, int gx, int c, int* t0, int* t1) {
   const int base = n / gx, rem = n % gx;
   *t0 = c * base + (c < rem ? c : rem);
   *t1 = *t0 + base + (c < rem ? 1 : 0);
+}
+
+// shape check incl. shared memory with the largest reduction state (top-k, k = KMAX)
+inline bool tensor_supported(const psbax_paths_t* p, bool bf16) {
+  if (!(p->G == 1 && p->S >= 16 && p->L > 0 && p->d <= TC_MAX_D)) return false;
+  Layout l{};
+  l.mode = bf16 ? MODE_TENSOR_BF16 : MODE_TENSOR;
+  l.dp4 = (p->d <= 2) ? 2 : round_up(p->d, 4);
+  l.OS = round_up(l.dp4 + 1, 4);
+  l.Kp = round_up(round_up(p->L, 8) + round_up(p->n, 8), TK);
+  return tc_smem_layout(l, EPI_TOPK, KMAX).total <= TC_SMEM_MAX;
 }
 
 inline int tensor_parts(const Layout& l, long long N, int sms) {
@@ -456,7 +484,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 28);
 
   const int nkb = lay.Kp / TK;
-  constexpr int OS = (DP + 1 + 3) / 4 * 4;  // == lay.OS for this DP (compile-time row stride)
+  constexpr bool GEN = (DP == 0);           // generic d: x in shared memory, table blocks streamed
+  constexpr int OSC = (DP + 1 + 3) / 4 * 4; // row stride of the table for this DP (compile time)
+  const int OS = GEN ? lay.OS : OSC;
+  constexpr int NSB = GEN ? TC_NSB_GENERIC : C::NSB;
+  const uint32_t STAGE = GEN ? sl.stage : (uint32_t)C::BBYTES;  // compile-time for the register-x kernels
+  float* sX = reinterpret_cast<float*>(smem + sl.x);
   const int s0 = blockIdx.y * TN;
   const int npass = (a.ntiles + TC_TILES - 1) / TC_TILES;
   int t0, t1;  // this CTA's contiguous range of passes (pairs of row tiles)
@@ -465,12 +498,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
 
   // ---- one-time setup ----
   {
-    const float4* src = reinterpret_cast<const float4*>(a.pack + lay.off_ft);
-    for (int i = tid; i < lay.Kp * OS / 4; i += TC_THREADS) reinterpret_cast<float4*>(sFT)[i] = __ldg(src + i);
+    if constexpr (!GEN) {
+      const float4* src = reinterpret_cast<const float4*>(a.pack + lay.off_ft);
+      for (int i = tid; i < lay.Kp * OS / 4; i += TC_THREADS) reinterpret_cast<float4*>(sFT)[i] = __ldg(src + i);
+    }
     for (int i = tid; i < round_up(lay.dp4, 4); i += TC_THREADS) sIl[i] = __ldg(a.pack + lay.off_invls + i);
   }
   if (tid == 0) {
-    for (int i = 0; i < C::NSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    // generic d: the producers read the streamed table block, so they release the stage too
+    for (int i = 0; i < NSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], GEN ? 1 + TC_NPROD : 1); }
     for (int i = 0; i < C::NSA; ++i) { mbar_init(&a_full[i], TC_NPROD); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], TC_NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -491,15 +527,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     // ================= B loader =================
     const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.pack + lay.off_tc) +
                         (size_t)blockIdx.y * nkb * C::BBYTES;
+    const uint8_t* gFT = reinterpret_cast<const uint8_t*>(a.pack + lay.off_ft);
+    const uint32_t ftbytes = (uint32_t)TK * OS * 4;
     uint32_t it = 0;
     for (int pass = t0; pass < t1; ++pass) {
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const uint32_t bs = it % C::NSB, ph = (it / C::NSB) & 1;
+        const uint32_t bs = it % NSB, ph = (it / NSB) & 1;
         if (lane == 0) mbar_wait(&b_empty[bs], ph ^ 1);
         __syncwarp();
         if (elect_one()) {
-          mbar_arrive_expect_tx(&b_full[bs], C::BBYTES);
-          bulk_g2s(sB + bs * C::BBYTES, gB + (size_t)kb * C::BBYTES, C::BBYTES, &b_full[bs]);
+          mbar_arrive_expect_tx(&b_full[bs], C::BBYTES + (GEN ? ftbytes : 0u));
+          bulk_g2s(sB + bs * STAGE, gB + (size_t)kb * C::BBYTES, C::BBYTES, &b_full[bs]);
+          if constexpr (GEN)
+            bulk_g2s(sB + bs * STAGE + C::BBYTES, gFT + (size_t)kb * ftbytes, ftbytes, &b_full[bs]);
         }
         __syncwarp();
       }
@@ -519,12 +559,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
       tc_fence_after();
       const uint32_t d_addr = tmem + TC_COL_D + buf * (TC_TILES * TN);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const uint32_t bs = it % C::NSB;
+        const uint32_t bs = it % NSB;
         const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
         TC_TRACE(0, it, 0);
         if (!ready) {
           if (lane == 0) {
-            mbar_wait(&b_full[bs], (it / C::NSB) & 1);
+            mbar_wait(&b_full[bs], (it / NSB) & 1);
             mbar_wait(&a_full[as], aph);
           }
           __syncwarp();
@@ -532,7 +572,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         TC_TRACE(0, it, 1);
         tc_fence_after();
         const uint32_t a_base = tmem + TC_COL_A + as * (TC_TILES * C::ACT);
-        const uint32_t bbase = smem_u32(sB + bs * C::BBYTES);
+        const uint32_t bbase = smem_u32(sB + bs * STAGE);
 #pragma unroll
         for (int t = 0; t < TC_TILES; ++t) {
           if (t == TC_TILES - 1) {  // probe block it + 1 while tile 0's MMAs are queued
@@ -540,7 +580,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             uint32_t ok = 0;
             if (lane == 0)
               ok = (mbar_test(&a_full[nit % C::NSA], (nit / C::NSA) & 1) &&
-                    mbar_test(&b_full[nit % C::NSB], (nit / C::NSB) & 1)) ? 1u : 0u;
+                    mbar_test(&b_full[nit % NSB], (nit / NSB) & 1)) ? 1u : 0u;
             ready = __shfl_sync(0xffffffffu, ok, 0) != 0;
           }
           if (elect_one()) {
@@ -580,12 +620,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     (void)tracer;
     uint32_t it = 0;
     for (int pass = t0; pass < t1; ++pass) {
-      float x[TC_TILES][DP];
+      float x[TC_TILES][GEN ? 1 : DP];
+      if constexpr (GEN) {
+        // stage the pass's 256 rows transposed: sX[tile][i][row]; producer-only named barrier
+        constexpr int PT = TC_NPROD * 32;
+        const int ptid = tid - TC_PROD_WARP0 * 32;
+        asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");  // everyone done with the previous tile
+        const long long base = (long long)pass * TC_TILES * TM * lay.d;
+        const long long lim = a.N * lay.d;
+        for (int idx = ptid; idx < TC_TILES * TM * lay.d; idx += PT) {
+          const int rr = idx / lay.d, i = idx - rr * lay.d;  // rr in [0, 256)
+          sX[((rr >> 7) * lay.dp4 + i) * TM + (rr & 127)] = (base + idx < lim) ? __ldg(a.X + base + idx) : 0.f;
+        }
+        for (int idx = ptid; idx < TC_TILES * TM * (lay.dp4 - lay.d); idx += PT) {
+          const int rr = idx % (TC_TILES * TM), i = lay.d + idx / (TC_TILES * TM);
+          sX[((rr >> 7) * lay.dp4 + i) * TM + (rr & 127)] = 0.f;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
+      } else {
 #pragma unroll
-      for (int t = 0; t < TC_TILES; ++t) {
-        const long long row = ((long long)pass * TC_TILES + t) * TM + q * 32 + lane;
+        for (int t = 0; t < TC_TILES; ++t) {
+          const long long row = ((long long)pass * TC_TILES + t) * TM + q * 32 + lane;
 #pragma unroll
-        for (int i = 0; i < DP; ++i) x[t][i] = (row < a.N && i < lay.d) ? __ldg(a.X + row * lay.d + i) : 0.f;
+          for (int i = 0; i < DP; ++i) x[t][i] = (row < a.N && i < lay.d) ? __ldg(a.X + row * lay.d + i) : 0.f;
+        }
       }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
@@ -593,18 +651,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         if (tracer) TC_TRACE(1, it, 0);
         constexpr int NG = TC_FPW / 8;
         uint32_t s1[NG][TC_TILES][C::WCOLS], s2[NG][TC_TILES][C::WCOLS];
+        const uint32_t bs = it % NSB;
+        if constexpr (GEN) {  // the table block of this K-block arrives with the B image
+          if (lane == 0) mbar_wait(&b_full[bs], (it / NSB) & 1);
+          __syncwarp();
+        }
+        const float* ftb = GEN ? reinterpret_cast<const float*>(sB + bs * STAGE + C::BBYTES) + h * TC_FPW * OS
+                               : sFT + kbase0 * OS;
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           // 8 features for both tiles' rows: each table row is fetched once and used twice.
           // The RFF / kernel-feature branch is warp-uniform (sections are multiples of 8).
           const int kbase = kbase0 + g * 8;
-          const float* ft = sFT + kbase * OS;
+          const float* ft = ftb + g * 8 * OS;
           float v[TC_TILES][8];
-          if (kbase < lay.Lp_ft) {
+          if constexpr (GEN) {
+            // x from shared memory, 4 dimensions at a time, reused by the 8 features
+            const bool rff = kbase < lay.Lp_ft;
+            float acc[TC_TILES][8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float w[OS];
-              load_row<OS>(ft + j * OS, w);
+              const float b0 = rff ? ft[j * OS + lay.dp4] : 0.f;
+#pragma unroll
+              for (int t = 0; t < TC_TILES; ++t) acc[t][j] = b0;
+            }
+            const float* xr = sX + q * 32 + lane;
+            for (int i0 = 0; i0 < lay.dp4; i0 += 4) {
+              float xa[TC_TILES][4];
+#pragma unroll
+              for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  xa[t][c] = xr[(t * lay.dp4 + i0 + c) * TM];
+                  if (!rff) xa[t][c] *= sIl[i0 + c];
+                }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
+                const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    if (rff) {
+                      acc[t][j] = fmaf(xa[t][c], wv4[c], acc[t][j]);
+                    } else {
+                      const float df = xa[t][c] + wv4[c];
+                      acc[t][j] = fmaf(df, df, acc[t][j]);
+                    }
+                  }
+              }
+            }
+            if (rff) {
+#pragma unroll
+              for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[t][j] = __cosf(acc[t][j]);
+            } else {
+#pragma unroll
+              for (int t = 0; t < TC_TILES; ++t) kernel_profile8(acc[t], v[t], lay.kernel);
+            }
+          } else if (kbase < lay.Lp_ft) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float w[OSC];
+              load_row<OSC>(ft + j * OSC, w);
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t) {
                 float arg = w[DP];
@@ -617,8 +728,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             float r2[TC_TILES][8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float w[OS];
-              load_row<OS>(ft + j * OS, w);
+              float w[OSC];
+              load_row<OSC>(ft + j * OSC, w);
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t) {
                 float acc = 0.f;
@@ -654,6 +765,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
               }
             }
           }
+        }
+        if constexpr (GEN) {  // done reading the streamed table block
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&b_empty[bs]);
         }
         if (tracer) TC_TRACE(1, it, 1);
         if (lane == 0) {
@@ -745,7 +860,7 @@ int tensor_launch_epi(const KArgs& a0, int sms, cudaStream_t st, char* err, size
   const Layout& l = a.lay;
   const int gx = tensor_parts(l, a.N, sms), gy = l.Sp / TN;
   const TcSmem sl = tc_smem_layout(l, EPI, a.k);
-  if (sl.total > 227 * 1024) {
+  if (sl.total > TC_SMEM_MAX) {
     snprintf(err, errlen, "tensor engine: shared memory %u B exceeds 227 KB (L + n or d too large)", sl.total);
     return PSBAX_E_UNSUPPORTED;
   }
@@ -756,15 +871,13 @@ int tensor_launch_epi(const KArgs& a0, int sms, cudaStream_t st, char* err, size
                               (int)sl.total);                                                           \
     if (ce == cudaSuccess) k_shared_tensor<DPV, EPI, BF><<<dim3(gx, gy), TC_THREADS, sl.total, st>>>(a);  \
   } while (0)
-  switch (l.dp4) {
+  switch (sl.generic ? 0 : l.dp4) {
     case 2: TC_LAUNCH(2); break;
     case 4: TC_LAUNCH(4); break;
     case 8: TC_LAUNCH(8); break;
     case 12: TC_LAUNCH(12); break;
     case 16: TC_LAUNCH(16); break;
-    default:
-      snprintf(err, errlen, "tensor engine: d=%d not supported", l.d);
-      return PSBAX_E_UNSUPPORTED;
+    default: TC_LAUNCH(0); break;  // generic d / large tables
   }
 #undef TC_LAUNCH
   if (ce == cudaSuccess) ce = cudaGetLastError();

@@ -47,3 +47,5 @@ def test_invalid_arguments_report_errors():
     assert lib.psbax_pack_bytes(C.byref(s), C.byref(n)) == 0 and n.value > 0
     s.engine = 2  # tensor engine needs a shared basis
     assert lib.psbax_pack_bytes(C.byref(s), C.byref(n)) == -2
+    s.engine = 3
+    assert lib.psbax_pack_bytes(C.byref(s), C.byref(n)) == -2

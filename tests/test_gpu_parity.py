@@ -33,6 +33,8 @@ CASES = [
     (1, 0, 3, 38, 1, "matern52", 100),          # posterior mean: L = 0
     (3, 40, 80, 12, 1, "rbf", 260),             # d = 80 (GB1 one-hot width), small-S route
     (24, 72, 80, 16, 1, "matern52", 200),       # d = 80 on the shared-basis route
+    (70, 1000, 32, 512, 1, "matern52", 1500),   # C3 shape (32-d embedding), generic-d tensor kernel
+    (64, 300, 80, 130, 1, "rbf", 700),          # d = 80, generic-d tensor kernel
     (2, 8, 1, 3, 2, "matern32", 33),            # tiny everything
 ]
 
@@ -43,7 +45,7 @@ def _tol(p):
 
 def _tensor_ok(c):
     S, L, d, n, G, kernel, N = c
-    return G == 1 and S >= 16 and L > 0 and d <= 16
+    return G == 1 and S >= 16 and L > 0 and d <= 128
 
 
 ENGINE_CASES = ([(c, "simt") for c in CASES] + [(c, "tensor") for c in CASES if _tensor_ok(c)] +
@@ -60,7 +62,13 @@ def case(request):
     key = request.param[0]
     if key not in _REF_CACHE:
         _REF_CACHE[key] = O.eval_paths(p, X.double()).numpy()  # [N, S] float64
-    return p, X, _REF_CACHE[key], to_batch(p, engine=engine)
+    try:
+        batch = to_batch(p, engine=engine)
+    except Exception as ex:  # e.g. 3xTF32 operands of a d = 80 problem do not fit shared memory
+        if "tensor engine needs" in str(ex):
+            pytest.skip(f"{engine}: shape not supported by this engine")
+        raise
+    return p, X, _REF_CACHE[key], batch
 
 
 def test_values(case):
@@ -323,10 +331,15 @@ def test_randomised_shapes_all_engines():
         ref = O.eval_paths(p, X.double()).numpy()
         tol = _tol(p)
         engines = ["simt"]
-        if G == 1 and S >= 16 and L > 0 and d <= 16:
+        if G == 1 and S >= 16 and L > 0:
             engines += ["tensor", "tensor_bf16"]
         for eng in engines:
-            b = to_batch(p, engine=eng)
+            try:
+                b = to_batch(p, engine=eng)
+            except Exception as ex:
+                if "tensor engine needs" in str(ex):
+                    continue
+                raise
             tag = (trial, eng, S, L, d, n, G, kernel, N)
             out = b.values(X.cuda()).double().cpu().numpy()
             assert (np.abs(out - ref).max(axis=0) <= tol).all(), tag
