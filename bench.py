@@ -82,7 +82,7 @@ class Clocks:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -253,6 +253,7 @@ def run_ours(args):
         masks_h, _b, cnt_h, _bv, _bi = e2e_step()
     sync_all()
     t_e2e = time.perf_counter() - e0
+    w1 = time.time()  # clocks are sampled over both timed loops (device-resident and end-to-end)
     assert int(cnt_h[0]) == int(res.count[0]), "streamed and resident level sets disagree"
     clk = clocks.stop(w0, w1) if rank == 0 else None
 

@@ -2,7 +2,6 @@
 // Host side: argument validation, operand-pack layout, launch configuration.
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 
 #include "sp_common.cuh"
@@ -175,7 +174,6 @@ int prepare(const psbax_paths_t* p, const void* pack, const float* X, int64_t N,
   a.N = N;
   a.ystd = p->y_std;
   a.c0 = (float)((double)p->y_std * (double)p->mean_const + (double)p->y_mean);
-  if (const char* dbg = getenv("PSBAX_TC_DEBUG")) a.debug = atoi(dbg);
   a.trace = g_trace;
   int gx, gy, nt;
   grid_for(a.lay, N, out->sms, &gx, &gy, &nt);

@@ -66,7 +66,6 @@ struct KArgs {
   int k;
   float* p_tv;
   int* p_ti;
-  int debug;  // PSBAX_TC_DEBUG bit mask (profiling experiments only; 0 in production)
   long long* trace;  // optional device buffer for clock64 traces (psbax_debug_trace_buffer)
 };
 

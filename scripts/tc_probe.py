@@ -1,5 +1,5 @@
-"""Timing probe for the tensor engine: level-set pass over a 2-D grid (config-2 shape) with the
-PSBAX_TC_DEBUG experiment mask taken from the environment.  Profiling aid, not a benchmark."""
+"""Timing probe: level-set pass over a 2-D grid (config-2 shape) for one engine.
+usage: tc_probe.py [grid] [engine] [reps].  Profiling aid, not a benchmark."""
 import os
 import sys
 import time
@@ -32,6 +32,6 @@ for _ in range(reps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
-clk_per_row = ms * 1e-3 * 148 * 1.965e9 / N
-print(f"debug={os.environ.get('PSBAX_TC_DEBUG', '0'):>3} engine={engine} N={N} {ms:8.3f} ms  "
+clk_per_row = ms * 1e-3 * 148 * 1.965e9 / N  # at the nominal 1965 MHz
+print(f"engine={engine} N={N} {ms:8.3f} ms  "
       f"{N * bench.S / ms / 1e6:8.2f} Gevals/s  {clk_per_row:7.1f} clk/row/SM  count0={int(r.count[0])}")
