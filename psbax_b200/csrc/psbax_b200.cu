@@ -79,7 +79,12 @@ Layout make_layout(const psbax_paths_t* p) {
     l.mode = MODE_TENSOR_BF16;  // AUTO: the faster split; both hold the 1e-4 contract
   else l.mode = MODE_SHARED_SIMT;
   l.Lp_ft = (l.mode == MODE_PERSAMPLE) ? 0 : l.Lp;
-  l.Kp = round_up(l.Lp_ft + l.np_, TK);
+  l.tkb = TK;
+  if (is_tensor_mode(l.mode)) {
+    l.tc_generic = tc_choose_generic(l) ? 1 : 0;
+    l.tkb = tc_tkb(l.mode == MODE_TENSOR_BF16, l.tc_generic != 0);
+  }
+  l.Kp = round_up(l.Lp_ft + l.np_, l.tkb);
   size_t off = 0;
   l.off_invls = off; off += round_up(l.dp4, 4);
   l.off_ft = off;    off += (size_t)l.Kp * l.OS;

@@ -41,6 +41,8 @@ struct Layout {
   int Kp;     // rows of ft / wv, multiple of TK
   int Sp;     // S rounded up to TN
   int mode;
+  int tkb;         // tensor engines: features per block (32, or 64 for BF16x3 with x in registers)
+  int tc_generic;  // tensor engines: x tile in shared memory + streamed table blocks
   size_t off_invls, off_ft, off_wv, off_pb, off_tc, total_floats;
 };
 

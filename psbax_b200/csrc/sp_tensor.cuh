@@ -39,46 +39,43 @@ namespace psbax {
 
 constexpr int TC_MAX_D = 128;           // d <= 16: x in registers; larger d: x tile in shared memory
 constexpr int TC_MAX_D_REG = 16;
-constexpr int TC_NSB_GENERIC = 4;       // B + feature-table ring depth of the generic-d kernels
 constexpr int TC_MAX_S = 1 << 20;  // any S: processed in chunks of 64 samples
 #ifndef PSBAX_TC_NPROD
 #define PSBAX_TC_NPROD 16
 #endif
-template <bool BF>
-struct TcCfg;
-template <>
-struct TcCfg<false> {  // 3xTF32
-  static constexpr int NSB = 4, NSA = 2;           // B (smem) and A (tmem) ring depths
-  static constexpr int BBYTES = 128 * TK * 4;      // 16 KB: 128 rows (split1|split2) x 32 k
-  static constexpr int ACT = 64;                   // A columns per tile per stage
-  static constexpr int KSTEPS = TK / 8;            // MMAs along k per block (K = 8)
-  static constexpr int KCOLS = 8;                  // A columns per k-step
-  static constexpr int B_KSTEP = 256;              // bytes: two 128-byte core matrices per k-step
-  static constexpr int B_SBO = 1024;               // bytes between 8-row groups
-  static constexpr int B_SPLIT2 = 8 * B_SBO;       // rows 64..127
-  static constexpr int WCOLS = 8;                  // A columns per 8 features per split
+// Operand-format / block-size configuration.  GEN = generic-d kernel (x tile in shared memory).
+template <bool BF, bool GEN>
+struct TcCfg {
+  // features per block (= per A / B stage).  BF16x3 with x in registers uses 64-feature blocks:
+  // same stage footprints as 3xTF32, half the synchronisation per feature (measured 10.0 -> 8.9 ms)
+  static constexpr int TKB = (BF && !GEN) ? 64 : 32;
+  static constexpr int ESZ = BF ? 2 : 4;                 // operand element bytes
+  static constexpr int KMMA = BF ? 16 : 8;               // K per MMA
+  static constexpr int BBYTES = 128 * TKB * ESZ;         // B image: 128 rows (split1|split2) x TKB
+  static constexpr int ACT = TKB * ESZ * 2 / 4;          // A columns per tile per stage (two splits)
+  static constexpr int NSA = 128 / ACT;                  // A ring depth: 256 TMEM columns / (2 tiles * ACT)
+  static constexpr int NSB = GEN ? 4 : (BBYTES == 16384 ? 4 : 8);  // B ring depth
+  static constexpr int KSTEPS = TKB / KMMA;              // MMAs along k per block
+  static constexpr int KCOLS = 8;                        // A columns per k-step
+  static constexpr int B_KSTEP = 256;                    // bytes: two 128-byte core matrices per k-step
+  static constexpr int B_SBO = TKB * ESZ * 8;            // bytes between 8-row groups
+  static constexpr int B_SPLIT2 = 8 * B_SBO;             // rows 64..127
+  static constexpr int WCOLS = BF ? 4 : 8;               // A columns per 8 features per split
 };
-template <>
-struct TcCfg<true> {  // BF16x3
-  static constexpr int NSB = 8, NSA = 4;
-  static constexpr int BBYTES = 128 * TK * 2;      // 8 KB
-  static constexpr int ACT = 32;
-  static constexpr int KSTEPS = TK / 16;           // K = 16
-  static constexpr int KCOLS = 8;
-  static constexpr int B_KSTEP = 256;
-  static constexpr int B_SBO = 512;
-  static constexpr int B_SPLIT2 = 8 * B_SBO;
-  static constexpr int WCOLS = 4;                  // 8 bf16 features = 4 packed columns
-};
-// warp roles.  The issue arbiter favours high warp ids (measured: epilogue warps placed BELOW the
-// producers were starved to ~5% IPC and became the critical path).  Bounded-work roles sit on
-// top: MMA issuer and loader (mostly parked), then the epilogue, the producers at the bottom.
+__host__ __device__ inline int tc_tkb(bool bf, bool generic) { return (bf && !generic) ? 64 : 32; }
+__host__ __device__ inline uint32_t tc_bbytes(bool bf, bool generic) { return 128u * tc_tkb(bf, generic) * (bf ? 2 : 4); }
+
+#ifndef PSBAX_TC_NPROD
+#define PSBAX_TC_NPROD 16
+#endif
+// warp roles: producers first (lane quarter = warp % 4), then the epilogue, the MMA issuer, the
+// loader and the TMEM allocator.  (Measured: the order of epilogue and producers does not matter;
+// the epilogue must simply be short enough to hide behind a pass — see profiles/r01_tuning_log.md.)
 constexpr int TC_PROD_WARP0 = 0, TC_NPROD = PSBAX_TC_NPROD;          // 8 or 16 producer warps
 constexpr int TC_EPI_WARP0 = TC_NPROD, TC_NEPI = 4;
 constexpr int TC_WARP_MMA = TC_EPI_WARP0 + TC_NEPI, TC_WARP_LOAD = TC_WARP_MMA + 1,
               TC_WARP_ALLOC = TC_WARP_MMA + 2;
 constexpr int TC_THREADS = (TC_WARP_MMA + 4) * 32;
-constexpr int TC_FPW = TK / (TC_NPROD / 4);                            // features per producer warp per block
 static_assert(TC_NPROD == 8 || TC_NPROD == 16, "8 or 16 producer warps");
 constexpr int TC_COL_D = 0, TC_COL_A = 256;
 constexpr int TC_TILES = 2;                  // row tiles per CTA pass
@@ -88,8 +85,8 @@ inline bool tensor_supported(const psbax_paths_t* p, bool bf16);
 inline bool is_tensor_mode(int mode) { return mode == MODE_TENSOR || mode == MODE_TENSOR_BF16; }
 // [chunks][nkb] images of BBYTES
 inline size_t tensor_pack_floats(const Layout& l) {
-  const size_t bb = (l.mode == MODE_TENSOR_BF16) ? TcCfg<true>::BBYTES : TcCfg<false>::BBYTES;
-  return (size_t)(l.Sp / TN) * (l.Kp / TK) * (bb / 4);
+  const bool bf = l.mode == MODE_TENSOR_BF16;
+  return (size_t)(l.Sp / TN) * (l.Kp / l.tkb) * (tc_bbytes(bf, l.tc_generic != 0) / 4);
 }
 
 // ---------------------------------------------------------------------------------
@@ -286,13 +283,14 @@ __host__ __device__ inline TcSmem tc_smem_layout_impl(const Layout& l, int epi, 
   const bool bf = l.mode == MODE_TENSOR_BF16;
   TcSmem s{};
   s.generic = generic;
-  const uint32_t bbytes = bf ? TcCfg<true>::BBYTES : TcCfg<false>::BBYTES;
-  s.nsb = s.generic ? TC_NSB_GENERIC : (bf ? TcCfg<true>::NSB : TcCfg<false>::NSB);
-  s.stage = bbytes + (s.generic ? (uint32_t)TK * l.OS * 4 : 0u);
+  const uint32_t tkb = tc_tkb(bf, generic), bbytes = tc_bbytes(bf, generic);
+  s.nsb = generic ? 4u : (bbytes == 16384u ? 4u : 8u);
+  s.stage = bbytes + (generic ? tkb * l.OS * 4 : 0u);
+  const uint32_t kp = (uint32_t)round_up(l.Lp + l.np_, (int)tkb);
   uint32_t o = 0;
   s.b = o;     o += s.nsb * s.stage;
-  s.ft = o;    o += s.generic ? 0u : (uint32_t)l.Kp * l.OS * 4;             // resident table (small d)
-  s.x = o;     o += s.generic ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u;   // x tile [tile][i][row]
+  s.ft = o;    o += generic ? 0u : kp * l.OS * 4;                         // resident table (small d)
+  s.x = o;     o += generic ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u;   // x tile [tile][i][row]
   s.out = o;   o += TN * OUT_LD * 4;
   s.state = o; o += (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;
   s.il = o;    o += (uint32_t)round_up(l.dp4, 4) * 4;
@@ -302,13 +300,15 @@ __host__ __device__ inline TcSmem tc_smem_layout_impl(const Layout& l, int epi, 
   return s;
 }
 constexpr uint32_t TC_SMEM_MAX = 227 * 1024;
-// resident feature table when it fits (d <= 16), else the generic kernel with streamed table blocks
+// Shape-only decision (the operand pack depends on it): resident feature table + x in registers
+// when d <= 16 and everything fits shared memory even with the largest reduction state, else the
+// generic kernel.  Needs l.mode, l.dp4, l.OS, l.Lp, l.np_.
+__host__ __device__ inline bool tc_choose_generic(const Layout& l) {
+  if (l.dp4 > TC_MAX_D_REG) return true;
+  return tc_smem_layout_impl(l, EPI_TOPK, KMAX, false).total > TC_SMEM_MAX;
+}
 __host__ __device__ inline TcSmem tc_smem_layout(const Layout& l, int epi, int k) {
-  if (l.dp4 <= TC_MAX_D_REG) {
-    const TcSmem r = tc_smem_layout_impl(l, epi, k, false);
-    if (r.total <= TC_SMEM_MAX) return r;
-  }
-  return tc_smem_layout_impl(l, epi, k, true);
+  return tc_smem_layout_impl(l, epi, k, l.tc_generic != 0);
 }
 
 // CTA c of gx handles the contiguous range [t0, t1) of passes
@@ -325,8 +325,10 @@ inline bool tensor_supported(const psbax_paths_t* p, bool bf16) {
   l.mode = bf16 ? MODE_TENSOR_BF16 : MODE_TENSOR;
   l.dp4 = (p->d <= 2) ? 2 : round_up(p->d, 4);
   l.OS = round_up(l.dp4 + 1, 4);
-  l.Kp = round_up(round_up(p->L, 8) + round_up(p->n, 8), TK);
-  return tc_smem_layout(l, EPI_TOPK, KMAX).total <= TC_SMEM_MAX;
+  l.Lp = round_up(p->L, 8);
+  l.np_ = round_up(p->n, 8);
+  const bool generic = tc_choose_generic(l);
+  return tc_smem_layout_impl(l, EPI_TOPK, KMAX, generic).total <= TC_SMEM_MAX;
 }
 
 inline int tensor_parts(const Layout& l, long long N, int sms) {
@@ -351,26 +353,24 @@ __device__ __forceinline__ uint16_t bf16_rn_bits(float x) { return (uint16_t)(cv
 
 __global__ void k_tensor_pack(Layout lay, float* __restrict__ pack) {
   const float* __restrict__ wv = pack + lay.off_wv;
-  const int nkb = lay.Kp / TK;
-  const size_t total = (size_t)(lay.Sp / TN) * nkb * 4096;
   const bool bf = lay.mode == MODE_TENSOR_BF16;
+  const int tkb = lay.tkb;
+  const int nkb = lay.Kp / tkb;
+  const int img_elems = 128 * tkb;                 // elements per image
+  const int kcore = bf ? 8 : 4;                    // elements per 16-byte core-matrix row
+  const int group_elems = 8 * tkb;                 // elements per 8-row group (SBO)
+  const size_t total = (size_t)(lay.Sp / TN) * nkb * img_elems;
   float* __restrict__ tc32 = pack + lay.off_tc;
   uint16_t* __restrict__ tc16 = reinterpret_cast<uint16_t*>(pack + lay.off_tc);
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
-    const int within = (int)(idx & 4095);
-    const size_t img = idx >> 12;
+    const int within = (int)(idx % img_elems);
+    const size_t img = idx / img_elems;
     const int kb = (int)(img % nkb), cy = (int)(img / nkb);
-    const int rg = within >> 8;
-    int r, k;
-    if (bf) {
-      r = rg * 8 + ((within >> 3) & 7);
-      k = ((within >> 6) & 3) * 8 + (within & 7);
-    } else {
-      r = rg * 8 + ((within >> 2) & 7);
-      k = ((within >> 5) & 7) * 4 + (within & 3);
-    }
-    const float x = wv[(size_t)(kb * TK + k) * lay.Sp + cy * TN + (r & 63)];
+    const int rg = within / group_elems, rem = within % group_elems;
+    const int kc = rem / (8 * kcore), r8 = (rem / kcore) & 7, ke = rem % kcore;
+    const int r = rg * 8 + r8, k = kc * kcore + ke;
+    const float x = wv[(size_t)(kb * tkb + k) * lay.Sp + cy * TN + (r & 63)];
     if (bf) {
       const uint16_t b1 = bf16_rn_bits(x);
       const float x1 = __uint_as_float((uint32_t)b1 << 16);
@@ -461,7 +461,7 @@ __device__ __forceinline__ void epilogue_levelset_reg_flush(const KArgs& a, LsRe
 // ---------------------------------------------------------------------------------
 template <int DP, int EPI, bool BF>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_constant__ KArgs a) {
-  using C = TcCfg<BF>;
+  using C = TcCfg<BF, DP == 0>;
   // no-swizzle UMMA operands only need 16-byte alignment; plain array arithmetic keeps the
   // shared address space visible to the compiler (LDS/STS instead of generic LD/ST)
   extern __shared__ __align__(128) uint8_t tc_smem[];
@@ -483,11 +483,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   uint64_t* d_empty = bars + 26;       // [2]
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 28);
 
-  const int nkb = lay.Kp / TK;
+  constexpr int TKB = C::TKB;
+  constexpr int TC_FPW = TKB / (TC_NPROD / 4);  // features per producer warp per block
+  const int nkb = lay.Kp / TKB;
   constexpr bool GEN = (DP == 0);           // generic d: x in shared memory, table blocks streamed
   constexpr int OSC = (DP + 1 + 3) / 4 * 4; // row stride of the table for this DP (compile time)
   const int OS = GEN ? lay.OS : OSC;
-  constexpr int NSB = GEN ? TC_NSB_GENERIC : C::NSB;
+  constexpr int NSB = C::NSB;
   const uint32_t STAGE = GEN ? sl.stage : (uint32_t)C::BBYTES;  // compile-time for the register-x kernels
   float* sX = reinterpret_cast<float*>(smem + sl.x);
   const int s0 = blockIdx.y * TN;
@@ -528,7 +530,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.pack + lay.off_tc) +
                         (size_t)blockIdx.y * nkb * C::BBYTES;
     const uint8_t* gFT = reinterpret_cast<const uint8_t*>(a.pack + lay.off_ft);
-    const uint32_t ftbytes = (uint32_t)TK * OS * 4;
+    const uint32_t ftbytes = (uint32_t)TKB * OS * 4;
     uint32_t it = 0;
     for (int pass = t0; pass < t1; ++pass) {
       for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -647,9 +649,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
       }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
-        const int kbase0 = kb * TK + h * TC_FPW;
+        const int kbase0 = kb * TKB + h * TC_FPW;
         if (tracer) TC_TRACE(1, it, 0);
         constexpr int NG = TC_FPW / 8;
+        // EARLY: wait for the stage after the first 8-feature group and store every group at once
+        // (lower register pressure: large DP / generic d); otherwise compute all groups before the
+        // wait, so that its latency hides behind the math (measured better for small d)
+        constexpr bool EARLY = GEN || DP >= 12;
         uint32_t s1[NG][TC_TILES][C::WCOLS], s2[NG][TC_TILES][C::WCOLS];
         const uint32_t bs = it % NSB;
         if constexpr (GEN) {  // the table block of this K-block arrives with the B image
@@ -765,32 +771,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
               }
             }
           }
+          if (EARLY ? (g == 0) : (g == NG - 1)) {
+            if (tracer) TC_TRACE(1, it, 1);
+            if (lane == 0) mbar_wait(&a_empty[as], aph ^ 1);
+            __syncwarp();
+            if (tracer) TC_TRACE(1, it, 2);
+            tc_fence_after();
+          }
+          if (EARLY || g == NG - 1) {
+#pragma unroll
+            for (int gg = EARLY ? g : 0; gg <= g; ++gg)
+#pragma unroll
+              for (int t = 0; t < TC_TILES; ++t) {
+                const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + (h * NG + gg) * C::WCOLS;
+                if constexpr (BF) {
+                  tc_st4(lane_addr + col, s1[gg][t]);
+                  tc_st4(lane_addr + col + C::ACT / 2, s2[gg][t]);
+                } else {
+                  tc_st8(lane_addr + col, s1[gg][t]);
+                  tc_st8(lane_addr + col + C::ACT / 2, s2[gg][t]);
+                }
+              }
+          }
         }
         if constexpr (GEN) {  // done reading the streamed table block
           __syncwarp();
           if (lane == 0) mbar_arrive(&b_empty[bs]);
         }
-        if (tracer) TC_TRACE(1, it, 1);
-        if (lane == 0) {
-          if constexpr (BF) mbar_wait_relaxed(&a_empty[as], aph ^ 1);
-          else mbar_wait(&a_empty[as], aph ^ 1);
-        }
-        __syncwarp();
-        if (tracer) TC_TRACE(1, it, 2);
-        tc_fence_after();
-#pragma unroll
-        for (int g = 0; g < NG; ++g)
-#pragma unroll
-          for (int t = 0; t < TC_TILES; ++t) {
-            const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + (h * NG + g) * C::WCOLS;
-            if constexpr (BF) {
-              tc_st4(lane_addr + col, s1[g][t]);
-              tc_st4(lane_addr + col + C::ACT / 2, s2[g][t]);
-            } else {
-              tc_st8(lane_addr + col, s1[g][t]);
-              tc_st8(lane_addr + col + C::ACT / 2, s2[g][t]);
-            }
-          }
         tc_wait_st();
         if (tracer) TC_TRACE(1, it, 3);
         tc_fence_before();
@@ -871,7 +878,7 @@ int tensor_launch_epi(const KArgs& a0, int sms, cudaStream_t st, char* err, size
                               (int)sl.total);                                                           \
     if (ce == cudaSuccess) k_shared_tensor<DPV, EPI, BF><<<dim3(gx, gy), TC_THREADS, sl.total, st>>>(a);  \
   } while (0)
-  switch (sl.generic ? 0 : l.dp4) {
+  switch (l.tc_generic ? 0 : l.dp4) {
     case 2: TC_LAUNCH(2); break;
     case 4: TC_LAUNCH(4); break;
     case 8: TC_LAUNCH(8); break;
