@@ -213,6 +213,20 @@ __device__ __forceinline__ void tc_st4(uint32_t taddr, const uint32_t (&v)[4]) {
                "r"(v[1]), "r"(v[2]), "r"(v[3])
                : "memory");
 }
+// packed fp32x2 arithmetic (FFMA2 on sm_100): one instruction for the two row tiles of a thread
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 // {hi16, lo16} = {bf16(a), bf16(b)}, round to nearest even
 __device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
   uint32_t d;
@@ -622,7 +636,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     (void)tracer;
     uint32_t it = 0;
     for (int pass = t0; pass < t1; ++pass) {
-      float x[TC_TILES][GEN ? 1 : DP];
+      static_assert(TC_TILES == 2, "the packed-FMA producers pair the two row tiles of a pass");
+      uint64_t xp[GEN ? 1 : DP];  // (x of tile 0, x of tile 1) per dimension
       if constexpr (GEN) {
         // stage the pass's 256 rows transposed: sX[tile][i][row]; producer-only named barrier
         constexpr int PT = TC_NPROD * 32;
@@ -640,11 +655,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         }
         asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
       } else {
+        const long long row0 = (long long)pass * TC_TILES * TM + q * 32 + lane, row1 = row0 + TM;
 #pragma unroll
-        for (int t = 0; t < TC_TILES; ++t) {
-          const long long row = ((long long)pass * TC_TILES + t) * TM + q * 32 + lane;
-#pragma unroll
-          for (int i = 0; i < DP; ++i) x[t][i] = (row < a.N && i < lay.d) ? __ldg(a.X + row * lay.d + i) : 0.f;
+        for (int i = 0; i < DP; ++i) {
+          const float x0 = (row0 < a.N && i < lay.d) ? __ldg(a.X + row0 * lay.d + i) : 0.f;
+          const float x1 = (row1 < a.N && i < lay.d) ? __ldg(a.X + row1 * lay.d + i) : 0.f;
+          xp[i] = pack2(x0, x1);
         }
       }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -722,13 +738,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             for (int j = 0; j < 8; ++j) {
               float w[OSC];
               load_row<OSC>(ft + j * OSC, w);
+              uint64_t arg = pack2(w[DP], w[DP]);
 #pragma unroll
-              for (int t = 0; t < TC_TILES; ++t) {
-                float arg = w[DP];
-#pragma unroll
-                for (int i = 0; i < DP; ++i) arg = fmaf(x[t][i], w[i], arg);
-                v[t][j] = __cosf(arg);
-              }
+              for (int i = 0; i < DP; ++i) arg = ffma2(xp[i], pack2(w[i], w[i]), arg);
+              float a0, a1;
+              unpack2(arg, a0, a1);
+              v[0][j] = __cosf(a0);
+              v[1][j] = __cosf(a1);
             }
           } else {
             float r2[TC_TILES][8];
@@ -736,16 +752,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             for (int j = 0; j < 8; ++j) {
               float w[OSC];
               load_row<OSC>(ft + j * OSC, w);
+              uint64_t acc = pack2(0.f, 0.f);
 #pragma unroll
-              for (int t = 0; t < TC_TILES; ++t) {
-                float acc = 0.f;
-#pragma unroll
-                for (int i = 0; i < DP; ++i) {
-                  const float df = fmaf(x[t][i], sIl[i], w[i]);
-                  acc = fmaf(df, df, acc);
-                }
-                r2[t][j] = acc;
+              for (int i = 0; i < DP; ++i) {
+                const uint64_t df = ffma2(xp[i], pack2(sIl[i], sIl[i]), pack2(w[i], w[i]));
+                acc = ffma2(df, df, acc);
               }
+              unpack2(acc, r2[0][j], r2[1][j]);
             }
 #pragma unroll
             for (int t = 0; t < TC_TILES; ++t) kernel_profile8(r2[t], v[t], lay.kernel);
