@@ -50,7 +50,9 @@ enum { /* psbax_paths_t.kernel */
   PSBAX_KERNEL_RBF = 0,
   PSBAX_KERNEL_MATERN12 = 1,
   PSBAX_KERNEL_MATERN32 = 2,
-  PSBAX_KERNEL_MATERN52 = 3
+  PSBAX_KERNEL_MATERN52 = 3,
+  PSBAX_KERNEL_LINEAR = 4 /* kappa(x, x') = (x*inv_ls) . Xtrain_j: the DKGP / LinearKernel path
+                             (src/utils.py:153-206); no RFF basis exists for it, use L = 0 */
 };
 
 enum { /* psbax_paths_t.engine: which kernel family evaluates a shared basis.  AUTO picks

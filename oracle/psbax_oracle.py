@@ -52,7 +52,7 @@ import torch
 
 DTYPE = torch.float64
 
-KERNEL_IDS = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3}
+KERNEL_IDS = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3, "linear": 4}
 KERNEL_NU = {"matern12": 0.5, "matern32": 1.5, "matern52": 2.5}
 
 
@@ -282,6 +282,27 @@ def draw_matheron_paths(gp: GPState, S: int, L: int = 1000, generator=None) -> P
         mean_const=gp.mean_const, y_mean=gp.y_mean, y_std=gp.y_std)
 
 
+def draw_dkgp_linear_paths(emb_train: torch.Tensor, y: torch.Tensor, variance: float, noise: float,
+                           mean_const: float, S: int, generator=None) -> PathParams:
+    """``get_function_samples`` DKGP / LinearKernel branch (``src/utils.py:186-206``) with
+    ``get_linear_weight_dist`` (``src/utils.py:153-182``):  Sn^-1 = I / v + E^T E / sigma^2,
+    mn = Sn^-1 \\ (E^T (y - mu)) / sigma^2,  w ~ N(mn, Sn)  (``MultivariateNormal(precision_matrix=Sn_inv)``);
+    f(X) = emb(X) @ w + mu.  The model is fitted on targets standardized by the caller
+    (``src/fit_model.py:76-79``), so no outcome transform is applied.  Returned on the EMBEDDING
+    space: evaluate with ``eval_paths(p, emb(X))``."""
+    E = emb_train.to(DTYPE)
+    y = y.to(DTYPE).reshape(-1)
+    h = E.shape[1]
+    Sn_inv = torch.eye(h, dtype=DTYPE) / variance + E.T @ E / noise
+    mn = torch.linalg.solve(Sn_inv, E.T @ (y - mean_const)) / noise
+    Sn = torch.linalg.inv(Sn_inv)
+    Lc = torch.linalg.cholesky(0.5 * (Sn + Sn.T))
+    W = mn[None, :] + torch.randn(S, h, dtype=DTYPE, generator=generator) @ Lc.T
+    return PathParams(omega=torch.zeros(1, 0, h, dtype=DTYPE), bias=torch.zeros(1, 0, dtype=DTYPE),
+                      W=torch.zeros(S, 0, dtype=DTYPE), kernel="linear", Xtrain=torch.eye(h, dtype=DTYPE),
+                      inv_ls=torch.ones(h, dtype=DTYPE), V=W, mean_const=mean_const, y_mean=0.0, y_std=1.0)
+
+
 def posterior_mean_params(gp: GPState) -> PathParams:
     """``PosteriorMean(model)`` as the S=1, L=0 special case:
     mu(x) = mean_const + k(x, X) (K + sigma2 I)^-1 (y - mean_const)
@@ -321,8 +342,11 @@ def eval_paths(p: PathParams, X: torch.Tensor, chunk: int = 8192) -> torch.Tenso
             f = torch.zeros(Xc.shape[0], p.S, dtype=DTYPE)
         if p.n > 0:
             Z = Xc * p.inv_ls
-            r2 = ((Z[:, None, :] - p.Xtrain[None, :, :]) ** 2).sum(-1)
-            f = f + kernel_profile(r2, p.kernel) @ p.V.T
+            if p.kernel == "linear":  # gpytorch LinearKernel: k(x, x') = x . x'
+                f = f + (Z @ p.Xtrain.T) @ p.V.T
+            else:
+                r2 = ((Z[:, None, :] - p.Xtrain[None, :, :]) ** 2).sum(-1)
+                f = f + kernel_profile(r2, p.kernel) @ p.V.T
         out[a:a + chunk] = p.y_mean + p.y_std * (p.mean_const + f)
     return out
 
@@ -340,20 +364,27 @@ def eval_path_grad(p: PathParams, X: torch.Tensor, s: int) -> torch.Tensor:
     f = torch.cos(Xc @ sub.omega[0].T + sub.bias[0]) @ sub.W[0] if sub.L > 0 else 0.0 * Xc.sum(-1)
     if sub.n > 0:
         Z = Xc * sub.inv_ls
-        r2 = ((Z[:, None, :] - sub.Xtrain[None, :, :]) ** 2).sum(-1)
-        f = f + kernel_profile(r2 + 1e-300, sub.kernel) @ sub.V[0]
+        if sub.kernel == "linear":
+            f = f + (Z @ sub.Xtrain.T) @ sub.V[0]
+        else:
+            r2 = ((Z[:, None, :] - sub.Xtrain[None, :, :]) ** 2).sum(-1)
+            f = f + kernel_profile(r2 + 1e-300, sub.kernel) @ sub.V[0]
     y = sub.y_mean + sub.y_std * (sub.mean_const + f)
     (g,) = torch.autograd.grad(y.sum(), X)
     return g
 
 
-def path_scale(p: PathParams) -> torch.Tensor:
+def path_scale(p: PathParams, X: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Per-sample magnitude the 1e-4 tolerance is relative to:
-    y_std * max(1, ||W_s||_2 + ||V_s||_2) — the natural forward-error scale of
-    the two dot products (|cos| <= 1, |kappa| <= 1)."""
+    y_std * max(1, ||W_s||_2 + m * ||V_s||_2) — the natural forward-error scale of
+    the two dot products.  |cos| <= 1 and |kappa| <= 1 give m = 1; the linear kernel's
+    features x . x' are unbounded, there m = max |feature| over the candidates X."""
     s = p.W.norm(dim=1) if p.L > 0 else torch.zeros(p.S, dtype=DTYPE)
     if p.n > 0:
-        s = s + p.V.norm(dim=1)
+        m = 1.0
+        if p.kernel == "linear" and X is not None:
+            m = max(1.0, float(((X.to(DTYPE) * p.inv_ls) @ p.Xtrain.T).abs().max()))
+        s = s + m * p.V.norm(dim=1)
     return abs(p.y_std) * torch.clamp(s, min=1.0)
 
 

@@ -47,7 +47,7 @@ int validate(const psbax_paths_t* p) {
   if (p->L + p->n < 1) return fail(PSBAX_E_INVALID, "L + n must be >= 1");
   if (p->G != 1 && p->G != p->S)
     return fail(PSBAX_E_INVALID, "G=%d must be 1 (shared basis) or S=%d", p->G, p->S);
-  if (p->kernel < PSBAX_KERNEL_RBF || p->kernel > PSBAX_KERNEL_MATERN52)
+  if (p->kernel < PSBAX_KERNEL_RBF || p->kernel > PSBAX_KERNEL_LINEAR)
     return fail(PSBAX_E_INVALID, "unknown kernel id %d", p->kernel);
   if (p->L > 0 && (!p->omega || !p->bias || !p->W))
     return fail(PSBAX_E_INVALID, "omega / bias / W must be non-NULL when L > 0");
@@ -71,8 +71,15 @@ Layout make_layout(const psbax_paths_t* p) {
   l.OSB = round_up(l.dp4 + 2, 4);
   l.Lp = round_up(p->L, 8);
   l.np_ = round_up(p->n, 8);
+  l.Lcos = l.Lp;
+  if (p->kernel == PSBAX_KERNEL_LINEAR) {  // the n linear rows join the feature section
+    l.lin_n = p->n;
+    l.n = 0;
+    l.np_ = 0;
+    l.Lp = l.Lcos + round_up(p->n, 8);
+  }
   l.Sp = round_up(p->S, TN);
-  const bool shared = (p->G == 1) && (p->S >= 16) && (p->L > 0);
+  const bool shared = (p->G == 1) && (p->S >= 16) && (l.Lp > 0);
   if (!shared) l.mode = MODE_PERSAMPLE;
   else if (p->engine == PSBAX_ENGINE_TENSOR) l.mode = MODE_TENSOR;
   else if (p->engine == PSBAX_ENGINE_TENSOR_BF16 || (p->engine == PSBAX_ENGINE_AUTO && tensor_supported(p, true)))

@@ -38,6 +38,8 @@ struct Layout {
   int Lp;     // L rounded up to 8
   int np_;    // n rounded up to 8
   int Lp_ft;  // RFF rows present in ft / wv (Lp in shared modes, 0 in per-sample mode)
+  int Lcos;   // feature rows below Lcos use cos(arg); rows in [Lcos, Lp) are linear-kernel rows: arg itself
+  int lin_n;  // number of linear-kernel rows (PSBAX_KERNEL_LINEAR), else 0
   int Kp;     // rows of ft / wv, multiple of TK
   int Sp;     // S rounded up to TN
   int mode;

@@ -136,10 +136,15 @@ __global__ void __launch_bounds__(128) k_eval_grad(const __grid_constant__ KArgs
     float arg = __ldg(r + dp4);
     for (int i = 0; i < d; ++i) arg = fmaf(sx[i], __ldg(r + i), arg);
     const float w = persample ? __ldg(r + dp4 + 1) : __ldg(WV + (size_t)l * lay.Sp + s);
-    float sn, cs;
-    sincosf(arg, &sn, &cs);
-    acc = fmaf(w, cs, acc);
-    coef[l] = -w * sn;
+    if (l >= lay.Lcos) {  // linear-kernel row: value w * arg, gradient w * omega
+      acc = fmaf(w, arg, acc);
+      coef[l] = w;
+    } else {
+      float sn, cs;
+      sincosf(arg, &sn, &cs);
+      acc = fmaf(w, cs, acc);
+      coef[l] = -w * sn;
+    }
   }
   const float* __restrict__ FTK = a.pack + lay.off_ft + (size_t)lay.Lp_ft * lay.OS;
   const float* __restrict__ VT = a.pack + lay.off_wv + (size_t)lay.Lp_ft * lay.Sp;

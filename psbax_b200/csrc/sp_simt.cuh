@@ -345,15 +345,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_shared_simt(const __grid_consta
           const int k = kbase + kk;
           const float* ft = sFT + k * OS;
           const bool rff = (kb * TK + k) < lay.Lp_ft;
+          const bool lin = (kb * TK + k) >= lay.Lcos;  // linear-kernel rows: identity activation
           float v;
           if constexpr (DP > 0) {
-            if (rff) v = __cosf(rff_arg<DP>(ft, x));
+            if (rff) { const float arg = rff_arg<DP>(ft, x); v = lin ? arg : __cosf(arg); }
             else v = kernel_profile(kern_r2<DP>(ft, xs), lay.kernel);
           } else {
             if (rff) {
               float arg = ft[dp4];
               for (int i = 0; i < dp4; ++i) arg = fmaf(sX[i * TM + grow], ft[i], arg);
-              v = __cosf(arg);
+              v = lin ? arg : __cosf(arg);
             } else {
               float r2 = 0.f;
               for (int i = 0; i < dp4; ++i) {
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_persample(const __grid_constant
 #pragma unroll
           for (int r = 0; r < R; ++r) {
             const float arg = fmaf(x[r][0], p.x, fmaf(x[r][1], p.y, p.z));
-            acc[r] = fmaf(p.w, __cosf(arg), acc[r]);
+            acc[r] = fmaf(p.w, (l >= lay.Lcos) ? arg : __cosf(arg), acc[r]);
           }
         }
       } else if constexpr (DP > 0) {
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_persample(const __grid_constant
             float arg = bw.x;
 #pragma unroll
             for (int i = 0; i < DP; ++i) arg = fmaf(x[r][i], om[i], arg);
-            acc[r] = fmaf(bw.y, __cosf(arg), acc[r]);
+            acc[r] = fmaf(bw.y, (l >= lay.Lcos) ? arg : __cosf(arg), acc[r]);
           }
         }
       } else {
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_persample(const __grid_constant
             }
           }
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = fmaf(ww, __cosf(arg[r]), acc[r]);
+          for (int r = 0; r < R; ++r) acc[r] = fmaf(ww, (l >= lay.Lcos) ? arg[r] : __cosf(arg[r]), acc[r]);
         }
       }
       // ---- exact-kernel part: sum_j V[s,j] * kappa(|x/ls - xt_j|) ----
@@ -660,6 +661,7 @@ __global__ void k_pack(Layout lay, const float* __restrict__ omega, const float*
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int d = lay.d, L = lay.L, n = lay.n, S = lay.S, dp4 = lay.dp4;
+  const int Lcos = lay.Lcos, lin_n = lay.lin_n;  // linear-kernel rows: omega := Xtrain * inv_ls, w := V
   // invls
   for (size_t i = t0; i < (size_t)round_up(dp4, 4); i += stride)
     pack[lay.off_invls + i] = (i < (size_t)d && inv_ls) ? inv_ls[i] : 0.f;
@@ -672,6 +674,7 @@ __global__ void k_pack(Layout lay, const float* __restrict__ omega, const float*
       float v = 0.f;
       if (row < Lpf) {
         if (row < L) v = (c < d) ? omega[(size_t)row * d + c] : (c == dp4 ? bias[row] : 0.f);
+        else if (row >= Lcos && row - Lcos < lin_n && c < d) v = Xtrain[(size_t)(row - Lcos) * d + c] * inv_ls[c];
       } else {
         const int j = row - Lpf;
         if (j < n && c < d) v = -Xtrain[(size_t)j * d + c];
@@ -689,6 +692,7 @@ __global__ void k_pack(Layout lay, const float* __restrict__ omega, const float*
       if (s < S) {
         if (row < Lpf) {
           if (row < L) v = W[(size_t)s * L + row];
+          else if (row >= Lcos && row - Lcos < lin_n) v = V[(size_t)s * lin_n + (row - Lcos)];
         } else {
           const int j = row - Lpf;
           if (j < n) v = V[(size_t)s * n + j];
@@ -711,6 +715,9 @@ __global__ void k_pack(Layout lay, const float* __restrict__ omega, const float*
         if (c < d) v = omega[((size_t)g * L + l) * d + c];
         else if (c == dp4) v = bias[(size_t)g * L + l];
         else if (c == dp4 + 1) v = W[(size_t)s * L + l];
+      } else if (l >= Lcos && l - Lcos < lin_n) {
+        if (c < d) v = Xtrain[(size_t)(l - Lcos) * d + c] * inv_ls[c];
+        else if (c == dp4 + 1) v = V[(size_t)s * lin_n + (l - Lcos)];
       }
       pack[lay.off_pb + idx] = v;
     }

@@ -334,13 +334,14 @@ __host__ __device__ inline void tc_tile_range(int n, int gx, int c, int* t0, int
 
 // shape check incl. shared memory with the largest reduction state (top-k, k = KMAX)
 inline bool tensor_supported(const psbax_paths_t* p, bool bf16) {
-  if (!(p->G == 1 && p->S >= 16 && p->L > 0 && p->d <= TC_MAX_D)) return false;
+  const bool lin = p->kernel == PSBAX_KERNEL_LINEAR;
+  if (!(p->G == 1 && p->S >= 16 && (p->L > 0 || (lin && p->n > 0)) && p->d <= TC_MAX_D)) return false;
   Layout l{};
   l.mode = bf16 ? MODE_TENSOR_BF16 : MODE_TENSOR;
   l.dp4 = (p->d <= 2) ? 2 : round_up(p->d, 4);
   l.OS = round_up(l.dp4 + 1, 4);
-  l.Lp = round_up(p->L, 8);
-  l.np_ = round_up(p->n, 8);
+  l.Lp = round_up(p->L, 8) + (lin ? round_up(p->n, 8) : 0);
+  l.np_ = lin ? 0 : round_up(p->n, 8);
   const bool generic = tc_choose_generic(l);
   return tc_smem_layout_impl(l, EPI_TOPK, KMAX, generic).total <= TC_SMEM_MAX;
 }
@@ -686,6 +687,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           // The RFF / kernel-feature branch is warp-uniform (sections are multiples of 8).
           const int kbase = kbase0 + g * 8;
           const float* ft = ftb + g * 8 * OS;
+          const bool lin = kbase >= lay.Lcos;  // linear-kernel rows: identity activation (warp-uniform)
           float v[TC_TILES][8];
           if constexpr (GEN) {
             // x from shared memory, 4 dimensions at a time, reused by the 8 features
@@ -730,7 +732,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[t][j] = __cosf(acc[t][j]);
+                for (int j = 0; j < 8; ++j) v[t][j] = lin ? acc[t][j] : __cosf(acc[t][j]);
             } else {
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t) kernel_profile8(acc[t], v[t], lay.kernel);
@@ -745,8 +747,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
               for (int i = 0; i < DP; ++i) arg = ffma2(xp[i], pack2(w[i], w[i]), arg);
               float a0, a1;
               unpack2(arg, a0, a1);
-              v[0][j] = __cosf(a0);
-              v[1][j] = __cosf(a1);
+              v[0][j] = lin ? a0 : __cosf(a0);
+              v[1][j] = lin ? a1 : __cosf(a1);
             }
           } else {
             float r2[TC_TILES][8];

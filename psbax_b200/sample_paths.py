@@ -64,7 +64,11 @@ class SamplePathBatch:
 
     def __init__(self, omega, bias, W, kernel: str = "matern52", Xtrain=None, inv_ls=None, V=None,
                  mean_const: float = 0.0, y_mean: float = 0.0, y_std: float = 1.0,
-                 device: Optional[torch.device] = None, engine: str = "auto"):
+                 device: Optional[torch.device] = None, engine: str = "auto", input_transform=None):
+        """``input_transform``: optional callable applied to the candidates on the GPU before the
+        evaluation (the DKGP embedding, ``src/utils.py:202``); the paths then live on its output
+        space (``d`` = embedding width)."""
+        self.input_transform = input_transform
         self.device = torch.device(device) if device is not None else default_device()
         if self.device.type != "cuda":
             raise PsbaxError("SamplePathBatch needs a CUDA device")
@@ -125,6 +129,9 @@ class SamplePathBatch:
 
     def _x(self, X) -> torch.Tensor:
         X = torch.as_tensor(X)
+        if self.input_transform is not None:
+            with torch.no_grad():
+                X = self.input_transform(X.reshape(-1, X.shape[-1]).to(self.device))
         if X.shape[-1] != self.d:
             raise PsbaxError(f"X has last dim {X.shape[-1]}, paths expect d={self.d}")
         X = X.reshape(-1, self.d)
@@ -334,15 +341,17 @@ class SamplePath:
                 self._single = SamplePathBatch(
                     b.omega[g:g + 1], b.bias[g:g + 1], b.W[s:s + 1], b.kernel, b.Xtrain, b.inv_ls,
                     None if b.V is None else b.V[s:s + 1], b.mean_const, b.y_mean, b.y_std,
-                    b.device, "simt")
+                    b.device, "simt", b.input_transform)
         return self._single
 
     def __call__(self, X) -> torch.Tensor:
         X = torch.as_tensor(X)
-        d = self.batch.d
+        d = X.shape[-1] if self.batch.input_transform is not None else self.batch.d
         if X.dim() == 3 and X.shape[1] != 1:
             raise PsbaxError("expected X of shape [b, 1, d] (q = 1)")
         if X.requires_grad:
+            if self.batch.input_transform is not None:
+                raise PsbaxError("gradients through an input transform are not implemented")
             flat = X.reshape(-1, d)
             return _PathValue.apply(flat, self)
         out = self._one().values(X.reshape(-1, d))[:, 0]
@@ -441,6 +450,42 @@ def posterior_mean_params(model, device=None) -> dict:
     return dict(omega=torch.zeros(1, 0, d), bias=torch.zeros(1, 0), W=torch.zeros(1, 0),
                 kernel=model.kernel, Xtrain=X / ls, inv_ls=1.0 / ls, V=(alpha * a)[None],
                 mean_const=mu, y_mean=y_mean, y_std=y_std)
+
+
+def dkgp_linear_params(model, S: int, generator: Optional[torch.Generator] = None, device=None) -> dict:
+    """DKGP with a linear kernel on the network embedding (``src/utils.py:153-206``): exact
+    weight-space draw  Sn^-1 = I / v + E^T E / sigma^2,  mn = Sn E^T (y - mu) / sigma^2,
+    w_s ~ N(mn, Sn),  f_s(x) = emb(x) . w_s + mu.  Expressed for the evaluator as L = 0 and h
+    linear-kernel rows Xtrain = I_h, V = W (kernel "linear"); the embedding is the batch's input
+    transform."""
+    dev = torch.device(device) if device is not None else default_device()
+    with torch.no_grad():
+        E = model.embedding(model.train_inputs[0].to(dev)).to(F64)  # [n, h]
+        y = model.train_targets.to(dev, F64)
+        h = E.shape[1]
+        v = float(model.covar_module.base_kernel.variance)
+        sigma2 = float(model.likelihood.noise.reshape(-1)[0])
+        mu = float(model.mean_module.constant)
+        Sn_inv = torch.eye(h, dtype=F64, device=dev) / v + E.T @ E / sigma2
+        mn = torch.linalg.solve(Sn_inv, E.T @ (y - mu)) / sigma2
+        Lp = torch.linalg.cholesky(Sn_inv)  # Sn = (Lp Lp^T)^-1  ->  w = mn + Lp^-T z
+        z = torch.randn(h, S, dtype=F64, device=dev, generator=generator)
+        W = (mn[:, None] + torch.linalg.solve_triangular(Lp.T, z, upper=True)).T  # [S, h]
+    return dict(omega=torch.zeros(1, 0, h), bias=torch.zeros(1, 0), W=torch.zeros(S, 0), kernel="linear",
+                Xtrain=torch.eye(h, dtype=F64), inv_ls=torch.ones(h, dtype=F64), V=W, mean_const=mu,
+                y_mean=0.0, y_std=1.0)
+
+
+def draw_dkgp_linear_paths(model, S: int, generator=None, device=None, engine: str = "auto") -> SamplePathBatch:
+    dev = torch.device(device) if device is not None else default_device()
+    net = model.feature_extractor.to(dev) if getattr(model, "feature_extractor", None) is not None else None
+
+    def embed(X):
+        X = X.to(dev, next(net.parameters()).dtype) if net is not None else X.to(dev)
+        return (net(X) if net is not None else X).to(F32)
+
+    return SamplePathBatch(**dkgp_linear_params(model, S, generator, dev), device=dev, engine=engine,
+                           input_transform=embed)
 
 
 def draw_matheron_paths(model, S: int, L: int = 1000, generator=None, device=None,

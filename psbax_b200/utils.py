@@ -8,8 +8,8 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .sample_paths import (SamplePath, SamplePathBatch, draw_matheron_paths, draw_reference_paths,
-                           posterior_mean_path)
+from .sample_paths import (SamplePath, SamplePathBatch, draw_dkgp_linear_paths, draw_matheron_paths,
+                           draw_reference_paths, posterior_mean_path)
 
 NUM_RFF_FEATURES = 1000  # hard-coded in the reference (src/utils.py:215,227,240)
 
@@ -25,6 +25,9 @@ def get_function_sample_batch(model, num_samples: int, **kwargs) -> SamplePathBa
     L = kwargs.get("num_rff_features", NUM_RFF_FEATURES)
     gen = kwargs.get("generator", None)
     device = kwargs.get("device", None)
+    from .models.deep_kernel_gp import DKGP
+    if isinstance(model, DKGP):  # linear kernel on the embedding: exact weight-space draw (utils.py:186-206)
+        return draw_dkgp_linear_paths(model, num_samples, gen, device, kwargs.get("engine", "auto"))
     if sampler == "matheron":
         return draw_matheron_paths(model, num_samples, L, gen, device, kwargs.get("engine", "auto"))
     if sampler == "reference":

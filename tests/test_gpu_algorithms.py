@@ -155,3 +155,41 @@ def test_posterior_mean_function():
     X = torch.rand(64, 3, dtype=torch.float64)
     mean, _ = O.gp_posterior(gp, X)
     assert (f(X.unsqueeze(1)) - mean).abs().max() < 1e-3 * gp.y_std
+
+
+def test_dkgp_linear_paths_topk():
+    """DKGP / LinearKernel branch (src/utils.py:153-206): exact weight-space draw on a network
+    embedding; the GPU path (embedding by the torch network, evaluation + top-k fused) against the
+    oracle's restatement evaluated on the same embedding and the same drawn weights."""
+    from psbax_b200.algorithms import TopK
+    from psbax_b200.models import DKGP
+    from psbax_b200.utils import get_function_sample_batch
+
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(3)
+    X = torch.rand(40, 12, dtype=torch.float64, generator=g)
+    y = torch.sin(X.sum(-1))
+    y = (y - y.mean()) / y.std()  # fit_model.py:76 standardizes before building the DKGP
+    model = DKGP(X, y, architecture=[12, 16, 8, 1])
+    model.train_model(X, y, lr=1e-2, num_iter=20)
+    paths = get_function_sample_batch(model, 24, generator=torch.Generator(device="cuda").manual_seed(1))
+    assert paths.kernel == "linear" and paths.L == 0 and paths.n == 8 and paths.d == 8
+    cand = torch.rand(500, 12, dtype=torch.float64, generator=g)
+    with torch.no_grad():
+        emb = model.embedding(cand).double().cpu()
+    p = O.PathParams(omega=torch.zeros(1, 0, 8, dtype=torch.float64), bias=torch.zeros(1, 0, dtype=torch.float64),
+                     W=torch.zeros(24, 0, dtype=torch.float64), kernel="linear", Xtrain=paths.Xtrain.double().cpu(),
+                     inv_ls=paths.inv_ls.double().cpu(), V=paths.V.double().cpu(),
+                     mean_const=float(np.float32(paths.mean_const)), y_mean=0.0, y_std=1.0)
+    ref = O.eval_paths(p, emb)  # [500, 24]
+    tol = 1e-4 * O.path_scale(p, emb) + 1e-5 * emb.abs().max() * p.V.abs().sum(1)  # embedding is fp32 on the GPU
+    vals = paths.values(cand).double().cpu()
+    assert ((vals - ref).abs().max(0).values <= tol).all()
+    algo = TopK({"x_path": cand.numpy(), "k": 5})
+    for s, (exe_path, out) in enumerate(algo.run_algorithm_on_batch(paths)):
+        order = torch.sort(ref[:, s], descending=True).values
+        if order[4] - order[5] > 2 * tol[s]:
+            assert set(exe_path.idx) == set(O.topk_reduce(ref[:, s], 5)[0].tolist())
+        assert out.shape == (5, 12)
+    f = paths.path(3)
+    assert (f(cand[:7].unsqueeze(1)) - ref[:7, 3]).abs().max() <= tol[3]

@@ -36,16 +36,21 @@ CASES = [
     (70, 1000, 32, 512, 1, "matern52", 1500),   # C3 shape (32-d embedding), generic-d tensor kernel
     (64, 300, 80, 130, 1, "rbf", 700),          # d = 80, generic-d tensor kernel
     (2, 8, 1, 3, 2, "matern32", 33),            # tiny everything
+    (64, 0, 32, 32, 1, "linear", 1000),         # DKGP / LinearKernel path (a2): h = 32 embedding, L = 0
+    (256, 0, 8, 8, 1, "linear", 700),           # linear rows only, x in registers
+    (20, 40, 5, 7, 1, "linear", 300),           # cos rows + linear rows in one table
+    (3, 16, 5, 7, 1, "linear", 200),            # small-S route
+    (4, 16, 5, 7, 4, "linear", 200),            # per-sample bases + linear rows
 ]
 
 
-def _tol(p):
-    return (REL * O.path_scale(p)).numpy()
+def _tol(p, X=None):
+    return (REL * O.path_scale(p, X)).numpy()
 
 
 def _tensor_ok(c):
     S, L, d, n, G, kernel, N = c
-    return G == 1 and S >= 16 and L > 0 and d <= 128
+    return G == 1 and S >= 16 and (L > 0 or kernel == "linear") and d <= 128
 
 
 ENGINE_CASES = ([(c, "simt") for c in CASES] + [(c, "tensor") for c in CASES if _tensor_ok(c)] +
@@ -76,12 +81,12 @@ def test_values(case):
     out = batch.values(X.cuda()).double().cpu().numpy()
     assert out.shape == ref.shape
     err = np.abs(out - ref).max(axis=0)
-    assert (err <= _tol(p)).all(), (err / _tol(p)).max()
+    assert (err <= _tol(p, X)).all(), (err / _tol(p, X)).max()
 
 
 def test_levelset(case):
     p, X, ref, batch = case
-    tol = _tol(p)
+    tol = _tol(p, X)
     for tau in (float(np.quantile(ref, 0.55)), float(ref.max() + 10.0), float(ref.min() - 10.0)):
         res = batch.levelset(X.cuda(), tau)
         mask = unpack_mask(res.mask, X.shape[0])  # [S, N]
@@ -110,7 +115,7 @@ def test_levelset(case):
 def test_argmax_only(case):
     p, X, ref, batch = case
     mv, am = batch.argmax(X.cuda(), row_offset=1000)
-    tol = _tol(p)
+    tol = _tol(p, X)
     best = ref.max(axis=0)
     assert (np.abs(mv.double().cpu().numpy() - best) <= tol).all()
     am = am.cpu().numpy() - 1000
@@ -123,7 +128,7 @@ def test_topk(case, k):
     N, S = ref.shape
     if k > N:
         pytest.skip("k > N")
-    tol = _tol(p)
+    tol = _tol(p, X)
     val, idx = batch.topk(X.cuda(), k)
     val, idx = val.double().cpu().numpy(), idx.cpu().numpy()
     for s in range(S):
@@ -200,7 +205,8 @@ def test_row_offset_and_sharded_merge_equal_whole(engine):
 
 def test_grad_matches_oracle():
     for (S, L, d, n, G, kernel) in [(4, 300, 3, 10, 1, "matern52"), (3, 100, 10, 20, 3, "rbf"),
-                                    (20, 64, 2, 8, 1, "matern32")]:
+                                    (20, 64, 2, 8, 1, "matern32"), (20, 16, 6, 6, 1, "linear"),
+                                    (2, 0, 6, 6, 1, "linear")]:
         p = random_params(S, L, d, n, G=G, kernel=kernel, seed=4)
         batch = to_batch(p)
         X = candidates(40, d)
@@ -211,8 +217,8 @@ def test_grad_matches_oracle():
             rows = (sidx == s).nonzero().reshape(-1)
             og = O.eval_path_grad(p, X[rows].double(), s).numpy()
             gnorm = max(1.0, float(np.abs(og).max()))
-            assert np.abs(g[rows].double().cpu().numpy() - og).max() <= 2e-4 * gnorm * float(O.path_scale(p)[s])
-            assert np.abs(val[rows].double().cpu().numpy() - ref[rows, s].numpy()).max() <= _tol(p)[s]
+            assert np.abs(g[rows].double().cpu().numpy() - og).max() <= 2e-4 * gnorm * float(O.path_scale(p, X)[s])
+            assert np.abs(val[rows].double().cpu().numpy() - ref[rows, s].numpy()).max() <= _tol(p, X)[s]
 
 
 def test_subset_select_matches_oracle():

@@ -193,3 +193,30 @@ def test_product_does_not_import_oracle():
             if fn.endswith(".py"):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_dkgp_linear_weight_draw_matches_oracle_moments():
+    """get_linear_weight_dist (src/utils.py:153-182): the product's draw (run on the CPU) has the
+    mean and covariance of the oracle's restatement."""
+    from psbax_b200.models import DKGP
+    from psbax_b200.sample_paths import dkgp_linear_params
+
+    torch.manual_seed(1)
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(30, 6, dtype=torch.float64, generator=g)
+    y = torch.cos(X.sum(-1) * 2)
+    y = (y - y.mean()) / y.std()
+    model = DKGP(X, y, architecture=[6, 10, 4, 1])
+    model.likelihood.noise = torch.tensor([0.05], dtype=torch.float64)
+    model.mean_module.constant = torch.tensor(0.1, dtype=torch.float64)
+    prm = dkgp_linear_params(model, 4000, torch.Generator().manual_seed(2), "cpu")
+    with torch.no_grad():
+        E = model.embedding(X).double()
+    ref = O.draw_dkgp_linear_paths(E, y, 1.0, 0.05, 0.1, 4000, torch.Generator().manual_seed(3))
+    Wp, Wo = prm["V"], ref.V
+    assert prm["kernel"] == "linear" and Wp.shape == (4000, 4)
+    se = Wo.std(0) / math.sqrt(4000)
+    assert ((Wp.mean(0) - Wo.mean(0)).abs() < 6 * se + 1e-9).all()
+    assert (torch.cov(Wp.T) - torch.cov(Wo.T)).abs().max() < 0.08 * float(torch.cov(Wo.T).abs().max())
+    with pytest.raises(AttributeError):
+        DKGP(X, y, architecture=[6, 1])  # reference quirk: no hidden layers -> AttributeError
