@@ -121,7 +121,7 @@ class SingleTaskGP:
         return ls.expand(d) if ls.numel() == 1 else ls
 
     def y_mean_std(self):
-        if self.outcome_transform is None:
+        if getattr(self, "outcome_transform", None) is None:
             return 0.0, 1.0
         return float(self.outcome_transform.means), float(self.outcome_transform.stdvs)
 

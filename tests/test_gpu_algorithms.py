@@ -193,3 +193,27 @@ def test_dkgp_linear_paths_topk():
         assert out.shape == (5, 12)
     f = paths.path(3)
     assert (f(cand[:7].unsqueeze(1)) - ref[:7, 3]).abs().max() <= tol[3]
+
+
+def test_info_bax_initialize_runs_the_batch_path():
+    """BAXAcquisitionFunction.initialize / run_algorithm_on_f_list (bax_acquisition.py:221-277):
+    exe_paths sample paths in one fused launch; the EIG of a q = 1 candidate is finite and the
+    conditioned models hold old data + path."""
+    from psbax_b200.acquisition_functions import BAXAcquisitionFunction
+    from psbax_b200.acquisition_functions.entropy import optimize_acqf_discrete
+    from psbax_b200.algorithms import TopK
+    from psbax_b200.utils import generate_random_points
+
+    gp = make_gp(8, 3, noise=1e-3)
+    model = _model_from(gp)
+    x_path = generate_random_points(100, 3, seed=1234).double()
+    algo = TopK({"x_path": x_path.numpy(), "k": 4})
+    acq = BAXAcquisitionFunction(model, algo, exe_paths=7)
+    acq.initialize(generator=torch.Generator(device="cuda").manual_seed(0), num_rff_features=128)
+    assert len(acq.exe_path_list) == 7 and len(acq.output_list) == 7 and len(acq.comb_model_list) == 7
+    assert all(o.shape == (4, 3) for o in acq.output_list)
+    assert acq.comb_model_list[0].train_inputs[0].shape == (12, 3)
+    vals = acq(x_path[:20].unsqueeze(1))
+    assert vals.shape == (20,) and torch.isfinite(vals).all() and (vals > -1e-6).all()
+    x_next, _ = optimize_acqf_discrete(acq, 2, x_path, max_batch_size=50)
+    assert x_next.shape == (2, 3)

@@ -220,3 +220,19 @@ def test_dkgp_linear_weight_draw_matches_oracle_moments():
     assert (torch.cov(Wp.T) - torch.cov(Wo.T)).abs().max() < 0.08 * float(torch.cov(Wo.T).abs().max())
     with pytest.raises(AttributeError):
         DKGP(X, y, architecture=[6, 1])  # reference quirk: no hidden layers -> AttributeError
+
+
+def test_fit_model_boundary():
+    from psbax_b200.fit_model import fit_model
+    from psbax_b200.models import DKGP, SingleTaskGP
+
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(16, 3, dtype=torch.float64, generator=g)
+    y = torch.sin(3 * X.sum(-1))
+    m = fit_model(X, y, "gp")
+    assert isinstance(m, SingleTaskGP) and m.kernel == "matern52" and m.covar_module.base_kernel.lengthscale.shape == (1, 3)
+    m2 = fit_model(X, y, "gp", kernel_type="rbf", state_dict={"lengthscale": 0.4, "outputscale": 1.0, "noise": 1e-3})
+    assert m2.kernel == "rbf" and float(m2.likelihood.noise) == 1e-3
+    m3 = fit_model(X, y, "dkgp", architecture=[8, 4], epochs=5)
+    assert isinstance(m3, DKGP) and m3.architecture == [3, 8, 4, 1]
+    assert fit_model(X, y, "nope") is None  # every failure returns None, as in the reference
