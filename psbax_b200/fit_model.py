@@ -22,10 +22,10 @@ def fit_model(inputs, outputs, model_type: str, **kwargs):
             model = SingleTaskGP(inputs, outputs, kernel=kernel, ard=kernel_type is None)
             state = kwargs.pop("state_dict", None)
             if state is not None:  # fixed model without training (:50-54)
-                model.covar_module.base_kernel.lengthscale = torch.as_tensor(state["lengthscale"]).reshape(1, -1).double()
-                model.covar_module.outputscale = torch.as_tensor(state["outputscale"]).double()
-                model.likelihood.noise = torch.as_tensor(state["noise"]).reshape(1).double()
-                model.mean_module.constant = torch.as_tensor(state.get("mean_const", 0.0)).double()
+                model.covar_module.base_kernel.lengthscale = torch.as_tensor(state["lengthscale"], dtype=torch.float64).reshape(1, -1)
+                model.covar_module.outputscale = torch.as_tensor(state["outputscale"], dtype=torch.float64)
+                model.likelihood.noise = torch.as_tensor(state["noise"], dtype=torch.float64).reshape(1)
+                model.mean_module.constant = torch.as_tensor(state.get("mean_const", 0.0), dtype=torch.float64)
                 return model
             return model.fit()
         if model_type == "dkgp":
