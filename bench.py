@@ -281,7 +281,7 @@ def run_ours(args):
         kern_s = (t_kern / K)
         achieved = flops_launch / kern_s / 1e12
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             torch.set_num_threads(cores)
             cpu_reference_pass(5_000, 1)
