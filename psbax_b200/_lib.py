@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PSBAX_LIB") or os.path.join(_HERE, "libpsbax_b200.so")
 
 KERNEL_IDS = {"rbf": 0, "matern12": 1, "matern32": 2, "matern52": 3, "linear": 4}
-ENGINE_IDS = {"auto": 0, "simt": 1, "tensor": 2, "tensor_bf16": 3}
+ENGINE_IDS = {"auto": 0, "simt": 1, "tensor": 2, "tensor_bf16": 3, "tensor_proj": 4}
 
 # every symbol include/psbax_b200.h declares
 EXPORTS = [

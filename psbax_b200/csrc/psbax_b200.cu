@@ -8,6 +8,7 @@
 #include "sp_extra.cuh"
 #include "sp_simt.cuh"
 #include "sp_tensor.cuh"
+#include "sp_tensor_proj.cuh"
 
 using namespace psbax;
 
@@ -53,13 +54,17 @@ int validate(const psbax_paths_t* p) {
     return fail(PSBAX_E_INVALID, "omega / bias / W must be non-NULL when L > 0");
   if (p->n > 0 && (!p->Xtrain || !p->inv_ls || !p->V))
     return fail(PSBAX_E_INVALID, "Xtrain / inv_ls / V must be non-NULL when n > 0");
-  if (p->engine < PSBAX_ENGINE_AUTO || p->engine > PSBAX_ENGINE_TENSOR_BF16)
+  if (p->engine < PSBAX_ENGINE_AUTO || p->engine > PSBAX_ENGINE_TENSOR_PROJ)
     return fail(PSBAX_E_INVALID, "unknown engine id %d", p->engine);
   if ((p->engine == PSBAX_ENGINE_TENSOR && !tensor_supported(p, false)) ||
       (p->engine == PSBAX_ENGINE_TENSOR_BF16 && !tensor_supported(p, true)))
     return fail(PSBAX_E_UNSUPPORTED,
                 "tensor engine needs a shared basis (G == 1), S >= 16, L > 0, d <= %d and operands that fit "
                 "shared memory (got G=%d d=%d S=%d L=%d n=%d)", TC_MAX_D, p->G, p->d, p->S, p->L, p->n);
+  if (p->engine == PSBAX_ENGINE_TENSOR_PROJ && !tensor_proj_supported(p))
+    return fail(PSBAX_E_UNSUPPORTED,
+                "tensor projection engine needs a shared basis (G == 1), S >= 16, L > 0, %d <= d <= %d and operands "
+                "that fit shared memory (got G=%d d=%d S=%d L=%d n=%d)", TP_MIN_D, TP_MAX_D, p->G, p->d, p->S, p->L, p->n);
   return PSBAX_OK;
 }
 
@@ -82,13 +87,21 @@ Layout make_layout(const psbax_paths_t* p) {
   const bool shared = (p->G == 1) && (p->S >= 16) && (l.Lp > 0);
   if (!shared) l.mode = MODE_PERSAMPLE;
   else if (p->engine == PSBAX_ENGINE_TENSOR) l.mode = MODE_TENSOR;
-  else if (p->engine == PSBAX_ENGINE_TENSOR_BF16 || (p->engine == PSBAX_ENGINE_AUTO && tensor_supported(p, true)))
+  else if (p->engine == PSBAX_ENGINE_TENSOR_BF16 || p->engine == PSBAX_ENGINE_TENSOR_PROJ ||
+           (p->engine == PSBAX_ENGINE_AUTO && tensor_supported(p, true)))
     l.mode = MODE_TENSOR_BF16;  // AUTO: the faster split; both hold the 1e-4 contract
   else l.mode = MODE_SHARED_SIMT;
   l.Lp_ft = (l.mode == MODE_PERSAMPLE) ? 0 : l.Lp;
   l.tkb = TK;
   if (is_tensor_mode(l.mode)) {
-    l.tc_generic = tc_choose_generic(l) ? 1 : 0;
+    const bool want_proj = p->engine == PSBAX_ENGINE_TENSOR_PROJ ||
+                           (p->engine == PSBAX_ENGINE_AUTO && p->d >= TP_AUTO_MIN_D);
+    if (want_proj && tp_supported(l)) {  // [W;V] images as for the generic kernel (32-feature bf16 blocks)
+      l.tc_proj = 1;
+      l.tc_generic = 1;
+    } else {
+      l.tc_generic = tc_choose_generic(l) ? 1 : 0;
+    }
     l.tkb = tc_tkb(l.mode == MODE_TENSOR_BF16, l.tc_generic != 0);
   }
   l.Kp = round_up(l.Lp_ft + l.np_, l.tkb);
@@ -99,6 +112,7 @@ Layout make_layout(const psbax_paths_t* p) {
   l.off_pb = off;    if (l.mode == MODE_PERSAMPLE) off += (size_t)l.S * l.Lp * l.OSB;
   off = (off + 63) / 64 * 64;  // 256-byte alignment for the tensor operands
   l.off_tc = off;    if (is_tensor_mode(l.mode)) off += tensor_pack_floats(l);
+  if (l.tc_proj) off += tp_pack_floats(l);  // Omega_aug images behind the [W;V] images
   l.total_floats = off;
   return l;
 }
@@ -239,6 +253,7 @@ int psbax_pack(const psbax_paths_t* paths, void* pack, size_t pack_bytes, void* 
   CUDA_TRY(cudaGetLastError());
   if (is_tensor_mode(l.mode)) {
     rc = tensor_pack(l, static_cast<float*>(pack), st);
+    if (rc == PSBAX_OK && l.tc_proj) rc = tensor_proj_pack(l, static_cast<float*>(pack), st);
     if (rc) return fail(rc, "tensor operand pack failed");
   }
   return PSBAX_OK;
@@ -274,7 +289,7 @@ int psbax_eval_values(const psbax_paths_t* paths, const void* pack, const float*
   pr.a.out = out;
   pr.a.ld_out = ld_out;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (is_tensor_mode(pr.a.lay.mode)) return tensor_launch(EPI_VALUES, pr.a, pr.sms, st, g_err, sizeof(g_err));
+  if (is_tensor_mode(pr.a.lay.mode)) return tensor_launch_any(EPI_VALUES, pr.a, pr.sms, st, g_err, sizeof(g_err));
   return dispatch_simt<EPI_VALUES>(pr.a, pr.grid, st);
 }
 
@@ -304,7 +319,7 @@ int psbax_eval_levelset(const psbax_paths_t* paths, const void* pack, const floa
   a.p_max = reinterpret_cast<float*>(a.p_cnt + per);
   a.p_arg = reinterpret_cast<int*>(a.p_max + per);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (is_tensor_mode(l.mode)) rc = tensor_launch(EPI_LEVELSET, a, pr.sms, st, g_err, sizeof(g_err));
+  if (is_tensor_mode(l.mode)) rc = tensor_launch_any(EPI_LEVELSET, a, pr.sms, st, g_err, sizeof(g_err));
   else rc = dispatch_simt<EPI_LEVELSET>(a, pr.grid, st);
   if (rc) return rc;
   k_levelset_finalize<<<(l.S + 127) / 128, 128, 0, st>>>(a.p_cnt, a.p_max, a.p_arg, parts, l.Sp, l.S,
@@ -337,7 +352,7 @@ int psbax_eval_topk(const psbax_paths_t* paths, const void* pack, const float* X
   a.p_tv = static_cast<float*>(workspace);
   a.p_ti = reinterpret_cast<int*>(a.p_tv + per);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (is_tensor_mode(l.mode)) rc = tensor_launch(EPI_TOPK, a, pr.sms, st, g_err, sizeof(g_err));
+  if (is_tensor_mode(l.mode)) rc = tensor_launch_any(EPI_TOPK, a, pr.sms, st, g_err, sizeof(g_err));
   else rc = dispatch_simt<EPI_TOPK>(a, pr.grid, st);
   if (rc) return rc;
   k_topk_merge<int><<<l.S, 128, 0, st>>>(a.p_tv, a.p_ti, parts, l.Sp, k, row_offset, out_val,

@@ -45,6 +45,7 @@ struct Layout {
   int mode;
   int tkb;         // tensor engines: features per block (32, or 64 for BF16x3 with x in registers)
   int tc_generic;  // tensor engines: x tile in shared memory + streamed table blocks
+  int tc_proj;     // BF16x3 engine, projection variant: feature arguments computed by 3xTF32 MMAs (sp_tensor_proj.cuh)
   size_t off_invls, off_ft, off_wv, off_pb, off_tc, total_floats;
 };
 

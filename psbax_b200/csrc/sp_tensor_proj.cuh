@@ -1,0 +1,538 @@
+// tcgen05 engine, projection variant (5 <= d <= 31): the feature arguments omega_l . x + b_l are
+// themselves computed by the tensor cores, so the producers only do MUFU + the operand split.
+//
+//   Z[256 rows x 32 features] = X_aug[256 x Kx] * Omega_aug^T[Kx x 32]      (3xTF32, fp32 accumulate)
+//       X_aug = (x_0..x_{d-1}, 1, 0..)  hi/lo TF32, written ONCE PER PASS into tensor memory by the
+//               producers (lane = row), A operand of the projection MMAs (TS mode)
+//       Omega_aug = (omega_l | bias_l | 0..) hi/lo TF32 images streamed by the loader behind the
+//               [W;V] image of the same 32-feature block, B operand
+//   producers: tcgen05.ld their 8 arguments x 2 tiles from Z, cos (or identity for linear-kernel
+//               rows; exact-kernel features still take the FFMA path from a shared-memory x tile),
+//               BF16x3 split, tcgen05.st into the A stage
+//   contraction and fused reductions as in k_shared_tensor (BF16x3, 32-feature blocks).
+//
+// Tensor-memory columns: D[tile] 0..127 (single-buffered: both tiles are drained to two shared
+// staging tiles before the reduction runs) | X[tile][split] 128..255 | Z[buf][tile] 256..383 |
+// A[stage][tile] 384..511.
+#pragma once
+#include "sp_tensor.cuh"
+
+namespace psbax {
+
+constexpr int TP_MIN_D = 5, TP_MAX_D = 31;
+constexpr int TP_AUTO_MIN_D = 8;  // AUTO uses the projection variant from this d on
+constexpr int TP_NSB_MAX = 8, TP_NSB_MIN = 3;  // operand ring depth: as deep as shared memory allows
+constexpr int TP_WARP_PROJ = TC_WARP_MMA + 3;  // the otherwise idle fourth service warp
+static_assert(TP_WARP_PROJ * 32 < TC_THREADS, "projection issuer warp");
+constexpr int TP_COL_D = 0, TP_COL_X = 128, TP_COL_Z = 256, TP_COL_A = 384;
+constexpr int TP_TKB = 32;
+constexpr int TP_WBYTES = 128 * TP_TKB * 2;  // bf16 [W;V] image of a block: 8 KB
+
+__host__ __device__ inline int tp_kx(int d) { return round_up(d + 1, 8); }
+__host__ __device__ inline uint32_t tp_obytes(int d) { return 2u * 32u * (uint32_t)tp_kx(d) * 4u; }  // hi + lo image
+
+struct TpSmem {
+  // `b`: ring of `nsb` stages = [W;V] image | Omega_aug images | the block's 32 rows of the feature
+  // table (only when the problem has exact-kernel rows; copied only for blocks that contain them)
+  uint32_t b, stage, nsb, ftk, x, out, state, il, bars, total;
+};
+__host__ __device__ inline TpSmem tp_smem_layout(const Layout& l, int epi, int k) {
+  TpSmem s{};
+  s.ftk = TP_WBYTES + tp_obytes(l.d);  // offset of the table block inside a stage
+  s.stage = s.ftk + (l.np_ > 0 ? (uint32_t)TP_TKB * l.OS * 4 : 0u);
+  // everything but the ring first; the ring takes what is left (a stage is released only after
+  // its contraction completes and a bulk copy takes ~2000 cycles, so depth 4 starved the issuers)
+  const uint32_t fixed = (l.n > 0 ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u) + TC_TILES * TN * OUT_LD * 4 +
+                         (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4 + (uint32_t)round_up(l.dp4, 4) * 4 +
+                         16 + 40 * 8;
+  uint32_t nsb = fixed < 227u * 1024u ? (227u * 1024u - fixed) / s.stage : 0u;
+  s.nsb = nsb > (uint32_t)TP_NSB_MAX ? (uint32_t)TP_NSB_MAX : nsb;
+  uint32_t o = 0;
+  s.b = o;     o += s.nsb * s.stage;
+  s.x = o;     o += l.n > 0 ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u;  // x tile for the kernel rows
+  s.out = o;   o += TC_TILES * TN * OUT_LD * 4;                       // two staging tiles
+  s.state = o; o += (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;
+  s.il = o;    o += (uint32_t)round_up(l.dp4, 4) * 4;
+  o = (o + 15) / 16 * 16;
+  s.bars = o;  o += 40 * 8;
+  s.total = o;
+  return s;
+}
+// shape rule for the projection variant (BF16x3 engine only)
+__host__ __device__ inline bool tp_supported(const Layout& l) {
+  if (l.mode != MODE_TENSOR_BF16 || l.d < TP_MIN_D || l.d > TP_MAX_D) return false;
+  const TpSmem sl = tp_smem_layout(l, EPI_TOPK, KMAX);
+  return sl.nsb >= (uint32_t)TP_NSB_MIN && sl.total <= TC_SMEM_MAX;
+}
+inline bool tensor_proj_supported(const psbax_paths_t* p) {
+  if (!tensor_supported(p, true)) return false;
+  const bool lin = p->kernel == PSBAX_KERNEL_LINEAR;
+  Layout l{};
+  l.mode = MODE_TENSOR_BF16;
+  l.d = p->d;
+  l.n = lin ? 0 : p->n;
+  l.dp4 = (p->d <= 2) ? 2 : round_up(p->d, 4);
+  l.OS = round_up(l.dp4 + 1, 4);
+  l.np_ = lin ? 0 : round_up(p->n, 8);
+  return tp_supported(l);
+}
+// floats appended to the tensor pack: one (hi | lo) Omega_aug image per 32-feature block
+__host__ __device__ inline size_t tp_pack_floats(const Layout& l) { return (size_t)(l.Kp / TP_TKB) * (tp_obytes(l.d) / 4); }
+
+// Omega_aug images: UMMA canonical no-swizzle K-major, N = 32 feature rows, K = Kx.
+//   float offset inside a split image: (r/8)*(Kx/4)*32 + (k/4)*32 + (r%8)*4 + (k%4)
+__global__ void k_tensor_proj_pack(Layout lay, float* __restrict__ pack, size_t off_om) {
+  const float* __restrict__ ft = pack + lay.off_ft;
+  float* __restrict__ om = pack + off_om;
+  const int kx = tp_kx(lay.d), nkb = lay.Kp / TP_TKB;
+  const int img = 32 * kx;  // floats per split image
+  const size_t total = (size_t)nkb * 2 * img;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int within = (int)(idx % img);
+    const int split = (int)((idx / img) & 1);
+    const int kb = (int)(idx / (2 * (size_t)img));
+    const int rg = within / (kx * 8), rem = within % (kx * 8);
+    const int kc = rem / 32, r8 = (rem >> 2) & 7, ke = rem & 3;
+    const int r = rg * 8 + r8, k = kc * 4 + ke;
+    const int row = kb * TP_TKB + r;  // feature row of the table
+    float x = 0.f;
+    if (row < lay.Lp_ft) {  // cos / linear rows: (omega | bias at dp4); kernel rows project to 0
+      if (k < lay.d) x = ft[(size_t)row * lay.OS + k];
+      else if (k == lay.d) x = ft[(size_t)row * lay.OS + lay.dp4];
+    }
+    const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    om[idx] = split == 0 ? hi : (x - hi);
+  }
+}
+
+inline int tensor_proj_pack(const Layout& l, float* pack, cudaStream_t st) {
+  const size_t off_om = l.off_tc + tensor_pack_floats(l);
+  k_tensor_proj_pack<<<148, 256, 0, st>>>(l, pack, off_om);
+  return cudaGetLastError() == cudaSuccess ? PSBAX_OK : PSBAX_E_CUDA;
+}
+
+// Waiting roles back off between probes: in this kernel the producers are NOT the bottleneck, and
+// twenty lanes re-polling mbarriers at full rate starve the MMA issuer's own barrier traffic in
+// the shared-memory sync unit (measured: 4600 cycles per block, MMAs or not).
+#ifndef TP_BACKOFF
+#define TP_BACKOFF 64
+#endif
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (TP_BACKOFF > 0) __nanosleep(TP_BACKOFF);
+    if (++spins > (1u << 24)) asm volatile("trap;");
+  }
+}
+
+// Warp-level wait for roles with many warps: one converged non-blocking probe by all lanes (the
+// common case: already complete, no divergence); only if that fails does lane 0 poll with
+// backoff while the others park at the reconvergence point (which costs a few hundred cycles).
+__device__ __forceinline__ void mbar_wait_hybrid(uint64_t* bar, uint32_t parity, int lane) {
+  if (!mbar_test(bar, parity)) {
+    if (lane == 0) mbar_wait_backoff(bar, parity);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_constant__ KArgs a, size_t off_om) {
+  using C = TcCfg<true, true>;  // BF16x3 contraction with 32-feature blocks
+  extern __shared__ __align__(128) uint8_t tp_smem[];
+  uint8_t* const smem = tp_smem;
+  const Layout& lay = a.lay;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const TpSmem sl = tp_smem_layout(lay, EPI, a.k);
+  uint8_t* sB = smem + sl.b;
+  float* sX = reinterpret_cast<float*>(smem + sl.x);
+  float* sOut = reinterpret_cast<float*>(smem + sl.out);
+  float* sState = reinterpret_cast<float*>(smem + sl.state);
+  float* sIl = reinterpret_cast<float*>(smem + sl.il);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
+  uint64_t* b_full = bars;         // [8]
+  uint64_t* b_empty = bars + 8;    // [8]
+  uint64_t* a_full = bars + 16;    // [2]
+  uint64_t* a_empty = bars + 18;   // [2]
+  uint64_t* z_full = bars + 20;    // [2]
+  uint64_t* z_empty = bars + 22;   // [2]
+  uint64_t* x_full = bars + 24;
+  uint64_t* x_empty = bars + 25;
+  uint64_t* d_full = bars + 26;
+  uint64_t* d_empty = bars + 27;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 28);
+  const uint32_t NSB = sl.nsb;
+
+  const int d = lay.d, OS = lay.OS, dp4 = lay.dp4;
+  const int kx = tp_kx(d);
+  const int nkb = lay.Kp / TP_TKB;
+  const uint32_t STAGE = sl.stage;
+  const uint32_t om_split = 32u * (uint32_t)kx * 4u;  // bytes per split image
+  const int s0 = blockIdx.y * TN;
+  const int npass = (a.ntiles + TC_TILES - 1) / TC_TILES;
+  int t0, t1;
+  tc_tile_range(npass, gridDim.x, blockIdx.x, &t0, &t1);
+  const EpiSmem e = epi_carve(sState, EPI, a.k);
+
+  for (int i = tid; i < round_up(dp4, 4); i += TC_THREADS) sIl[i] = __ldg(a.pack + lay.off_invls + i);
+  if (tid == 0) {
+    // the producers read the streamed table block, so they release the stage too
+    for (int i = 0; i < TP_NSB_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1 + TC_NPROD); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], TC_NPROD); mbar_init(&a_empty[i], 1);
+      mbar_init(&z_full[i], 1);        mbar_init(&z_empty[i], TC_NPROD);
+    }
+    mbar_init(x_full, TC_NPROD); mbar_init(x_empty, 1);
+    mbar_init(d_full, 1);        mbar_init(d_empty, TC_NEPI);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TC_WARP_ALLOC) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                 "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_NEPI) epi_init(e, EPI, a.k, tid - TC_EPI_WARP0 * 32, TC_NEPI * 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t total_blocks = (uint32_t)(t1 - t0) * (uint32_t)nkb;
+
+  if (warp == TC_WARP_LOAD) {
+    // ================= loader: [W;V] image + Omega_aug images of each block =================
+    const uint8_t* gW = reinterpret_cast<const uint8_t*>(a.pack + lay.off_tc) + (size_t)blockIdx.y * nkb * TP_WBYTES;
+    const uint8_t* gO = reinterpret_cast<const uint8_t*>(a.pack + off_om);
+    const uint8_t* gFT = reinterpret_cast<const uint8_t*>(a.pack + lay.off_ft);
+    const uint32_t obytes = tp_obytes(d), ftbytes = (uint32_t)TP_TKB * OS * 4;
+    uint32_t kb = 0, bs = 0, ph = 0;  // block inside the pass; ring stage and its phase
+    for (uint32_t it = 0; it < total_blocks; ++it) {
+      const bool has_kernel_rows = (int)(kb + 1) * TP_TKB > lay.Lp_ft;
+      TC_TRACE(3, it, 0);
+      mbar_wait_hybrid(&b_empty[bs], ph ^ 1, lane);
+      TC_TRACE(3, it, 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&b_full[bs], TP_WBYTES + obytes + (has_kernel_rows ? ftbytes : 0u));
+        bulk_g2s(sB + bs * STAGE, gW + (size_t)kb * TP_WBYTES, TP_WBYTES, &b_full[bs]);
+        bulk_g2s(sB + bs * STAGE + TP_WBYTES, gO + (size_t)kb * obytes, obytes, &b_full[bs]);
+        if (has_kernel_rows) bulk_g2s(sB + bs * STAGE + sl.ftk, gFT + (size_t)kb * ftbytes, ftbytes, &b_full[bs]);
+      }
+      __syncwarp();
+      if (++kb == (uint32_t)nkb) kb = 0;
+      if (++bs == NSB) { bs = 0; ph ^= 1; }
+    }
+  } else if (warp == TP_WARP_PROJ) {
+    // ================= projection issuer: Z[jt & 1] = X_aug * Omega_aug(block jt)^T =================
+    // The two MMA streams have their own warps: a single warp walking both wait -> issue ->
+    // commit chains was the critical path (~1800 cycles per block against ~1100 for the
+    // producers).  All lanes poll: a lane-0 poll leaves the warp diverged, and every
+    // reconvergence (WARPSYNC slow path) costs a latency-critical warp a few hundred cycles
+    // (measured 4600 -> 1800 cycles per block).  Counters instead of divisions, descriptors by
+    // addition from per-kernel bases.
+    constexpr uint32_t IDESC_P = umma_idesc_tf32(32);
+    const uint32_t sbo_o = (uint32_t)(kx / 4) * 128u;
+    // the 14-bit start-address field counts 16-byte units; stage offsets never carry out of it
+    const uint64_t dO0 = umma_desc_kmajor(smem_u32(sB) + TP_WBYTES, 128, sbo_o);
+    const uint32_t stage16 = STAGE >> 4, osplit16 = om_split >> 4;
+    const int nks = kx / 8;
+    const uint32_t nkb1 = (uint32_t)nkb - 1;
+    uint32_t jkb = 0, pl = 0, bs = 0, bph = 0;
+    for (uint32_t jt = 0; jt < total_blocks; ++jt) {
+      const uint32_t zb = jt & 1;
+      if (jkb == 0) mbar_wait(x_full, pl & 1);  // this pass's X operand is in tensor memory
+      mbar_wait(&b_full[bs], bph);
+      mbar_wait(&z_empty[zb], ((jt >> 1) & 1) ^ 1);
+      __syncwarp();
+      tc_fence_after();
+      TC_TRACE(0, jt, 4);
+      if (elect_one()) {
+        const uint64_t oh0 = dO0 + (uint64_t)(bs * stage16), ol0 = oh0 + osplit16;
+#pragma unroll
+        for (int t = 0; t < TC_TILES; ++t) {
+          const uint32_t dz = tmem + TP_COL_Z + (zb * TC_TILES + t) * 32;
+          const uint32_t xh = tmem + TP_COL_X + (t * 2) * 32, xl = xh + 32;
+          tc_mma_ts(dz, xh, oh0, IDESC_P, 0u);
+          tc_mma_ts(dz, xh, ol0, IDESC_P, 1u);
+          tc_mma_ts(dz, xl, oh0, IDESC_P, 1u);
+#pragma unroll 1
+          for (int ks = 1; ks < nks; ++ks) {
+            const uint64_t oh = oh0 + (uint64_t)(ks * 16), ol = ol0 + (uint64_t)(ks * 16);
+            tc_mma_ts(dz, xh + ks * 8, oh, IDESC_P, 1u);
+            tc_mma_ts(dz, xh + ks * 8, ol, IDESC_P, 1u);
+            tc_mma_ts(dz, xl + ks * 8, oh, IDESC_P, 1u);
+          }
+        }
+        tc_commit(&z_full[zb]);
+        if (jkb == nkb1) tc_commit(x_empty);  // last reader of this pass's X
+      }
+      __syncwarp();
+      TC_TRACE(0, jt, 5);
+      if (jkb == nkb1) { jkb = 0; ++pl; } else ++jkb;
+      if (++bs == NSB) { bs = 0; bph ^= 1; }
+    }
+  } else if (warp == TC_WARP_MMA) {
+    // ================= contraction issuer: D[tile] += A(block it) * [W;V](block it)^T =================
+    constexpr uint32_t IDESC_C = umma_idesc_bf16(TN);
+    const uint64_t dW0 = umma_desc_kmajor(smem_u32(sB), 128, C::B_SBO);
+    const uint32_t stage16 = STAGE >> 4;
+    const uint32_t nkb1 = (uint32_t)nkb - 1;
+    uint32_t kb = 0, pl = 0, bs = 0;
+    for (uint32_t it = 0; it < total_blocks; ++it) {
+      const bool last = kb == nkb1;
+      const uint32_t as = it & 1;
+      TC_TRACE(0, it, 0);
+      if (kb == 0) mbar_wait(d_empty, (pl & 1) ^ 1);
+      mbar_wait(&a_full[as], (it >> 1) & 1);  // (implies b_full: the projection of this block read the stage)
+      __syncwarp();
+      tc_fence_after();
+      TC_TRACE(0, it, 2);
+      if (elect_one()) {
+        const uint64_t b10 = dW0 + (uint64_t)(bs * stage16);
+#pragma unroll
+        for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+          for (int ks = 0; ks < C::KSTEPS; ++ks) {
+            const uint64_t b1 = b10 + (uint64_t)(ks * (C::B_KSTEP >> 4));
+            const uint64_t b2 = b1 + (uint64_t)(C::B_SPLIT2 >> 4);
+            const uint32_t a1 = tmem + TP_COL_A + (as * TC_TILES + t) * 32 + ks * 8, a2 = a1 + 16;
+            const uint32_t dd = tmem + TP_COL_D + t * TN;
+            tc_mma_ts_bf16(dd, a1, b1, IDESC_C, (kb | ks) ? 1u : 0u);
+            tc_mma_ts_bf16(dd, a1, b2, IDESC_C, 1u);
+            tc_mma_ts_bf16(dd, a2, b1, IDESC_C, 1u);
+          }
+        tc_commit(&a_empty[as]);
+        tc_commit(&b_empty[bs]);
+        if (last) tc_commit(d_full);
+      }
+      __syncwarp();
+      TC_TRACE(0, it, 3);
+      if (last) { kb = 0; ++pl; } else ++kb;
+      if (++bs == NSB) bs = 0;
+    }
+  } else if (warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_NPROD) {
+    // ================= producers =================
+    static_assert(TC_NPROD == 16, "projection variant: four producer warps per lane quarter");
+    const int q = warp & 3, h = (warp - TC_PROD_WARP0) >> 2;  // h: which 8 features; also which X part
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    constexpr int PT = TC_NPROD * 32;
+    const int ptid = tid - TC_PROD_WARP0 * 32;
+    uint32_t it = 0, bs = 0, bph = 0;
+    for (int pass = t0; pass < t1; ++pass) {
+      const uint32_t pl = (uint32_t)(pass - t0);
+      // ---- X operand of this pass: warp h writes tile (h >> 1), split (h & 1) of its rows ----
+      mbar_wait_hybrid(x_empty, (pl & 1) ^ 1, lane);
+      tc_fence_after();
+      {
+        const int t = h >> 1, split = h & 1;
+        const long long row = ((long long)pass * TC_TILES + t) * TM + q * 32 + lane;
+        const float* xr = a.X + row * d;
+        const bool ok = row < a.N;
+        for (int c = 0; c < kx / 8; ++c) {
+          uint32_t v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = c * 8 + j;
+            const float xv = (k < d) ? (ok ? __ldg(xr + k) : 0.f) : (k == d ? 1.0f : 0.f);
+            const uint32_t hb = __float_as_uint(xv) & 0xffffe000u;
+            v[j] = split == 0 ? hb : __float_as_uint(xv - __uint_as_float(hb));
+          }
+          tc_st8(lane_addr + TP_COL_X + (t * 2 + split) * 32 + c * 8, v);
+        }
+        tc_wait_st();
+      }
+      if (lay.n > 0) {  // plain x tile for the exact-kernel features
+        asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
+        const long long base = (long long)pass * TC_TILES * TM * d;
+        const long long lim = a.N * d;
+        for (int idx = ptid; idx < TC_TILES * TM * d; idx += PT) {
+          const int rr = idx / d, i = idx - rr * d;
+          sX[((rr >> 7) * dp4 + i) * TM + (rr & 127)] = (base + idx < lim) ? __ldg(a.X + base + idx) : 0.f;
+        }
+        asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(x_full);
+
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t as = it & 1, zb = it & 1, ph = (it >> 1) & 1;
+        const int kbase = kb * TP_TKB + h * 8;
+        // ---- arguments of this warp's 8 features x 2 tiles from the projection ----
+        if (warp == 0) TC_TRACE(1, it, 0);
+        mbar_wait_hybrid(&z_full[zb], ph, lane);
+        tc_fence_after();
+        if (warp == 0) TC_TRACE(1, it, 1);
+        uint32_t z[TC_TILES][8];
+#pragma unroll
+        for (int t = 0; t < TC_TILES; ++t) tc_ld8(lane_addr + TP_COL_Z + (zb * TC_TILES + t) * 32 + h * 8, z[t]);
+        tc_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&z_empty[zb]);
+        if (warp == 0) TC_TRACE(1, it, 2);
+        float v[TC_TILES][8];
+        if (kbase < lay.Lp_ft) {
+          const bool lin = kbase >= lay.Lcos;
+#pragma unroll
+          for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float arg = __uint_as_float(z[t][j]);
+              v[t][j] = lin ? arg : __cosf(arg);
+            }
+        } else {  // exact-kernel features: FFMA path (r^2 as a sum of squared differences)
+          // the block's table rows sit behind the operand images of the same stage (already
+          // landed: the projection MMAs of this block read the stage; the wait returns at once)
+          mbar_wait_hybrid(&b_full[bs], bph, lane);
+          const float* ft = reinterpret_cast<const float*>(sB + bs * STAGE + sl.ftk) + (size_t)(h * 8) * OS;
+          const float* xr = sX + q * 32 + lane;
+          float acc[TC_TILES][8];
+#pragma unroll
+          for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+          for (int i0 = 0; i0 < dp4; i0 += 4) {
+            float xa[TC_TILES][4];
+#pragma unroll
+            for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) xa[t][c] = xr[(t * dp4 + i0 + c) * TM] * sIl[i0 + c];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
+              const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+              for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const float df = xa[t][c] + wv4[c];
+                  acc[t][j] = fmaf(df, df, acc[t][j]);
+                }
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < TC_TILES; ++t) kernel_profile8(acc[t], v[t], lay.kernel);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&b_empty[bs]);
+        // ---- BF16x3 split, store into the A stage ----
+        uint32_t s1[TC_TILES][4], s2[TC_TILES][4];
+#pragma unroll
+        for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t p1 = cvt_bf16x2(v[t][2 * c + 1], v[t][2 * c]);
+            const uint64_t rr = ffma2(pack2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u)),
+                                      pack2(-1.0f, -1.0f), pack2(v[t][2 * c], v[t][2 * c + 1]));
+            float r0, r1;
+            unpack2(rr, r0, r1);
+            s1[t][c] = p1;
+            s2[t][c] = cvt_bf16x2(r1, r0);
+          }
+        if (warp == 0) TC_TRACE(1, it, 3);
+        mbar_wait_hybrid(&a_empty[as], ph ^ 1, lane);
+        tc_fence_after();
+        if (warp == 0) TC_TRACE(1, it, 4);
+#pragma unroll
+        for (int t = 0; t < TC_TILES; ++t) {
+          const uint32_t col = TP_COL_A + (as * TC_TILES + t) * 32 + h * 4;
+          tc_st4(lane_addr + col, s1[t]);
+          tc_st4(lane_addr + col + 16, s2[t]);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[as]);
+        if (warp == 0) TC_TRACE(1, it, 5);
+        if (++bs == NSB) { bs = 0; bph ^= 1; }
+      }
+    }
+  } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_NEPI) {
+    // ================= epilogue (D single-buffered: drain both tiles, release, then reduce) =================
+    const int q = warp & 3;
+    const int etid = tid - TC_EPI_WARP0 * 32;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    LsRegState<TC_NEPI> ls;
+    ls.init();
+    for (int pass = t0; pass < t1; ++pass) {
+      const uint32_t pl = (uint32_t)(pass - t0);
+      mbar_wait_hybrid(d_full, pl & 1, lane);
+      tc_fence_after();
+      const int r = q * 32 + lane;
+#pragma unroll 1
+      for (int t = 0; t < TC_TILES; ++t) {
+#pragma unroll 1
+        for (int c = 0; c < TN / 16; ++c) {
+          uint32_t u[16];
+          tc_ld16(lane_addr + TP_COL_D + t * TN + c * 16, u);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sOut[(t * TN + c * 16 + j) * OUT_LD + r] = __uint_as_float(u[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty);
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
+#pragma unroll 1
+      for (int t = 0; t < TC_TILES; ++t) {
+        const int tile = pass * TC_TILES + t;
+        if (tile < a.ntiles) {
+          const float* so = sOut + (size_t)t * TN * OUT_LD;
+          if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg<TC_NEPI>(a, so, ls, tile * TM, s0, etid);
+          else epilogue_tile<EPI, TC_NEPI>(a, so, e, tile * TM, s0, etid);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
+    }
+    if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg_flush<TC_NEPI>(a, ls, s0, etid);
+    else epilogue_flush<EPI>(a, e, s0, etid, TC_NEPI * 32);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_WARP_ALLOC) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+template <int EPI>
+int tensor_proj_launch_epi(const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
+  const Layout& l = a.lay;
+  const int gx = tensor_parts(l, a.N, sms), gy = l.Sp / TN;
+  const TpSmem sl = tp_smem_layout(l, EPI, a.k);
+  if (sl.total > TC_SMEM_MAX) {
+    snprintf(err, errlen, "tensor projection engine: shared memory %u B exceeds 227 KB", sl.total);
+    return PSBAX_E_UNSUPPORTED;
+  }
+  const size_t off_om = l.off_tc + tensor_pack_floats(l);
+  cudaError_t ce = cudaFuncSetAttribute(k_tensor_proj<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
+  if (ce == cudaSuccess) {
+    k_tensor_proj<EPI><<<dim3(gx, gy), TC_THREADS, sl.total, st>>>(a, off_om);
+    ce = cudaGetLastError();
+  }
+  if (ce != cudaSuccess) {
+    snprintf(err, errlen, "tensor projection engine launch failed: %s", cudaGetErrorString(ce));
+    return PSBAX_E_CUDA;
+  }
+  return PSBAX_OK;
+}
+
+inline int tensor_proj_launch(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
+  if (epi == EPI_VALUES) return tensor_proj_launch_epi<EPI_VALUES>(a, sms, st, err, errlen);
+  if (epi == EPI_LEVELSET) return tensor_proj_launch_epi<EPI_LEVELSET>(a, sms, st, err, errlen);
+  return tensor_proj_launch_epi<EPI_TOPK>(a, sms, st, err, errlen);
+}
+
+inline int tensor_launch_any(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
+  return a.lay.tc_proj ? tensor_proj_launch(epi, a, sms, st, err, errlen) : tensor_launch(epi, a, sms, st, err, errlen);
+}
+
+}  // namespace psbax

@@ -41,6 +41,9 @@ CASES = [
     (20, 40, 5, 7, 1, "linear", 300),           # cos rows + linear rows in one table
     (3, 16, 5, 7, 1, "linear", 200),            # small-S route
     (4, 16, 5, 7, 4, "linear", 200),            # per-sample bases + linear rows
+    (64, 500, 31, 40, 1, "matern52", 1300),     # largest d of the tensor-projection variant
+    (128, 333, 16, 0, 1, "rbf", 2049),          # projection variant, no kernel term, 2 chunks, ragged
+    (40, 64, 7, 200, 1, "matern32", 515),       # projection variant, kernel rows dominate
 ]
 
 
@@ -53,8 +56,13 @@ def _tensor_ok(c):
     return G == 1 and S >= 16 and (L > 0 or kernel == "linear") and d <= 128
 
 
+def _proj_ok(c):
+    return _tensor_ok(c) and 5 <= c[2] <= 31
+
+
 ENGINE_CASES = ([(c, "simt") for c in CASES] + [(c, "tensor") for c in CASES if _tensor_ok(c)] +
-                [(c, "tensor_bf16") for c in CASES if _tensor_ok(c)])
+                [(c, "tensor_bf16") for c in CASES if _tensor_ok(c)] +
+                [(c, "tensor_proj") for c in CASES if _proj_ok(c)])
 _REF_CACHE = {}
 
 
@@ -70,7 +78,7 @@ def case(request):
     try:
         batch = to_batch(p, engine=engine)
     except Exception as ex:  # e.g. 3xTF32 operands of a d = 80 problem do not fit shared memory
-        if "tensor engine needs" in str(ex):
+        if "engine needs" in str(ex):
             pytest.skip(f"{engine}: shape not supported by this engine")
         raise
     return p, X, _REF_CACHE[key], batch
@@ -270,13 +278,14 @@ def test_errors_are_reported():
         batch.values(candidates(10, 3).cuda())
 
 
-@pytest.mark.parametrize("engine", ["tensor", "tensor_bf16"])
+@pytest.mark.parametrize("engine", ["tensor", "tensor_bf16", "tensor_proj"])
 def test_tensor_engine_many_tiles_matches_simt(engine):
     """Several tiles per persistent CTA (accumulator double-buffering, barrier phase wrap-around)
     and several sample chunks: the tcgen05 engines against the FFMA engine and the oracle."""
-    p = random_params(100, 1000, 2, 64, seed=21)
+    d = 10 if engine == "tensor_proj" else 2
+    p = random_params(100, 1000, d, 64, seed=21)
     N = 148 * 128 * 5 + 77
-    X = candidates(N, 2).cuda()
+    X = candidates(N, d).cuda()
     bt, bs = to_batch(p, engine=engine), to_batch(p, engine="simt")
     vt, vs = bt.values(X), bs.values(X)
     tol = torch.from_numpy(_tol(p)).cuda().float()
@@ -339,11 +348,13 @@ def test_randomised_shapes_all_engines():
         engines = ["simt"]
         if G == 1 and S >= 16 and L > 0:
             engines += ["tensor", "tensor_bf16"]
+            if 5 <= d <= 31:
+                engines.append("tensor_proj")
         for eng in engines:
             try:
                 b = to_batch(p, engine=eng)
             except Exception as ex:
-                if "tensor engine needs" in str(ex):
+                if "engine needs" in str(ex):
                     continue
                 raise
             tag = (trial, eng, S, L, d, n, G, kernel, N)
