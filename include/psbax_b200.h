@@ -62,7 +62,7 @@ enum { /* psbax_paths_t.engine: which kernel family evaluates a shared basis.  A
   PSBAX_ENGINE_TENSOR = 2,      /* tcgen05 kernel, 3xTF32 operand split (G == 1 only) */
   PSBAX_ENGINE_TENSOR_BF16 = 3, /* tcgen05 kernel, BF16x3 operand split (G == 1 only) */
   PSBAX_ENGINE_TENSOR_PROJ = 4  /* BF16x3 kernel whose feature arguments omega.x + b are 3xTF32 tcgen05 MMAs
-                                   too (G == 1, 5 <= d <= 31); AUTO picks it for d >= 8 */
+                                   too (G == 1, 5 <= d <= 32); AUTO picks it whenever it applies */
 };
 
 /* The S sample paths.  Replaces the closure `get_gp_samples` returns

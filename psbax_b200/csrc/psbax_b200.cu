@@ -96,6 +96,7 @@ Layout make_layout(const psbax_paths_t* p) {
   if (is_tensor_mode(l.mode)) {
     const bool want_proj = p->engine == PSBAX_ENGINE_TENSOR_PROJ ||
                            (p->engine == PSBAX_ENGINE_AUTO && p->d >= TP_AUTO_MIN_D);
+    l.Kp = round_up(l.Lp_ft + l.np_, TP_TKB);  // what the projection variant would use (tp_supported reads it)
     if (want_proj && tp_supported(l)) {  // [W;V] images as for the generic kernel (32-feature bf16 blocks)
       l.tc_proj = 1;
       l.tc_generic = 1;

@@ -173,6 +173,17 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
   if (lane == 0) mbar_wait(bar, parity);
   __syncwarp();
 }
+// Warp-level wait for roles with many warps: one converged non-blocking probe by all lanes (the
+// common case: already complete, no divergence); only if that fails does lane 0 poll while the
+// others park at the reconvergence point.  A lane-0-only poll always leaves the warp diverged,
+// and the WARPSYNC slow path of the reconvergence costs a few hundred cycles per wait (ncu source
+// view of the projection kernel: half of the issuer warp's samples sat in those paths).
+__device__ __forceinline__ void mbar_wait_hybrid(uint64_t* bar, uint32_t parity, int lane) {
+  if (!mbar_test(bar, parity)) {
+    if (lane == 0) mbar_wait(bar, parity);
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -550,8 +561,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     for (int pass = t0; pass < t1; ++pass) {
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t bs = it % NSB, ph = (it / NSB) & 1;
-        if (lane == 0) mbar_wait(&b_empty[bs], ph ^ 1);
-        __syncwarp();
+        mbar_wait_hybrid(&b_empty[bs], ph ^ 1, lane);
         if (elect_one()) {
           mbar_arrive_expect_tx(&b_full[bs], C::BBYTES + (GEN ? ftbytes : 0u));
           bulk_g2s(sB + bs * STAGE, gB + (size_t)kb * C::BBYTES, C::BBYTES, &b_full[bs]);
@@ -563,7 +573,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     }
   } else if (warp == TC_WARP_MMA) {
     // ================= MMA issuer =================
-    // Lane 0 polls, the warp stays converged, one elected lane issues (straight UTC*MMA runs).
+    // All lanes poll (converged), one elected lane issues (straight UTC*MMA runs).
     // tcgen05.mma issue blocks while the tensor pipe's short queue is full, so the readiness of
     // the NEXT block is probed in the middle of the current one: its latency is then covered by
     // queued MMAs instead of draining the pipe at the block boundary.
@@ -572,7 +582,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     bool ready = false;
     for (int pass = t0; pass < t1; ++pass, ++tl) {
       const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
-      mbar_wait_warp(&d_empty[buf], dph ^ 1, lane);
+      mbar_wait(&d_empty[buf], dph ^ 1);  // all lanes poll: the single issuer warp stays converged
+      __syncwarp();
       tc_fence_after();
       const uint32_t d_addr = tmem + TC_COL_D + buf * (TC_TILES * TN);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -580,10 +591,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
         TC_TRACE(0, it, 0);
         if (!ready) {
-          if (lane == 0) {
-            mbar_wait(&b_full[bs], (it / NSB) & 1);
-            mbar_wait(&a_full[as], aph);
-          }
+          mbar_wait(&b_full[bs], (it / NSB) & 1);
+          mbar_wait(&a_full[as], aph);
           __syncwarp();
         }
         TC_TRACE(0, it, 1);
@@ -594,11 +603,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         for (int t = 0; t < TC_TILES; ++t) {
           if (t == TC_TILES - 1) {  // probe block it + 1 while tile 0's MMAs are queued
             const uint32_t nit = it + 1;
-            uint32_t ok = 0;
-            if (lane == 0)
-              ok = (mbar_test(&a_full[nit % C::NSA], (nit / C::NSA) & 1) &&
-                    mbar_test(&b_full[nit % NSB], (nit / NSB) & 1)) ? 1u : 0u;
-            ready = __shfl_sync(0xffffffffu, ok, 0) != 0;
+            const bool ok = mbar_test(&a_full[nit % C::NSA], (nit / C::NSA) & 1) &&
+                            mbar_test(&b_full[nit % NSB], (nit / NSB) & 1);
+            ready = __all_sync(0xffffffffu, ok) != 0;
           }
           if (elect_one()) {
 #pragma unroll
@@ -676,8 +683,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         uint32_t s1[NG][TC_TILES][C::WCOLS], s2[NG][TC_TILES][C::WCOLS];
         const uint32_t bs = it % NSB;
         if constexpr (GEN) {  // the table block of this K-block arrives with the B image
-          if (lane == 0) mbar_wait(&b_full[bs], (it / NSB) & 1);
-          __syncwarp();
+          mbar_wait_hybrid(&b_full[bs], (it / NSB) & 1, lane);
         }
         const float* ftb = GEN ? reinterpret_cast<const float*>(sB + bs * STAGE + C::BBYTES) + h * TC_FPW * OS
                                : sFT + kbase0 * OS;
@@ -793,8 +799,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           }
           if (EARLY ? (g == 0) : (g == NG - 1)) {
             if (tracer) TC_TRACE(1, it, 1);
-            if (lane == 0) mbar_wait(&a_empty[as], aph ^ 1);
-            __syncwarp();
+            mbar_wait_hybrid(&a_empty[as], aph ^ 1, lane);
             if (tracer) TC_TRACE(1, it, 2);
             tc_fence_after();
           }
@@ -837,7 +842,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     for (int pass = t0; pass < t1; ++pass, ++tl) {
       const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 0);
-      mbar_wait_warp(&d_full[buf], dph, lane);
+      mbar_wait_hybrid(&d_full[buf], dph, lane);
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 1);
       tc_fence_after();
       const int r = q * 32 + lane;

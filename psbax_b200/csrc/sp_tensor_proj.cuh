@@ -19,8 +19,8 @@
 
 namespace psbax {
 
-constexpr int TP_MIN_D = 5, TP_MAX_D = 31;
-constexpr int TP_AUTO_MIN_D = 8;  // AUTO uses the projection variant from this d on
+constexpr int TP_MIN_D = 5, TP_MAX_D = 32;
+constexpr int TP_AUTO_MIN_D = 5;  // AUTO uses the projection variant from this d on (measured: wins from d = 5)
 constexpr int TP_NSB_MAX = 8, TP_NSB_MIN = 3;  // operand ring depth: as deep as shared memory allows
 constexpr int TP_WARP_PROJ = TC_WARP_MMA + 3;  // the otherwise idle fourth service warp
 static_assert(TP_WARP_PROJ * 32 < TC_THREADS, "projection issuer warp");
@@ -28,13 +28,17 @@ constexpr int TP_COL_D = 0, TP_COL_X = 128, TP_COL_Z = 256, TP_COL_A = 384;
 constexpr int TP_TKB = 32;
 constexpr int TP_WBYTES = 128 * TP_TKB * 2;  // bf16 [W;V] image of a block: 8 KB
 
-__host__ __device__ inline int tp_kx(int d) { return round_up(d + 1, 8); }
+// K extent of the projection.  The bias rides as an extra column of X_aug (= 1) when the padding
+// to a multiple of 8 leaves room for it; for d % 8 == 0 the producers add it instead (keeps
+// d = 32 inside the 32 tensor-memory columns per X split).
+__host__ __device__ inline bool tp_bias_in_x(int d) { return (d % 8) != 0; }
+__host__ __device__ inline int tp_kx(int d) { return tp_bias_in_x(d) ? round_up(d + 1, 8) : d; }
 __host__ __device__ inline uint32_t tp_obytes(int d) { return 2u * 32u * (uint32_t)tp_kx(d) * 4u; }  // hi + lo image
 
 struct TpSmem {
   // `b`: ring of `nsb` stages = [W;V] image | Omega_aug images | the block's 32 rows of the feature
   // table (only when the problem has exact-kernel rows; copied only for blocks that contain them)
-  uint32_t b, stage, nsb, ftk, x, out, state, il, bars, total;
+  uint32_t b, stage, nsb, ftk, x, out, state, il, bias, bars, total;
 };
 __host__ __device__ inline TpSmem tp_smem_layout(const Layout& l, int epi, int k) {
   TpSmem s{};
@@ -44,7 +48,7 @@ __host__ __device__ inline TpSmem tp_smem_layout(const Layout& l, int epi, int k
   // its contraction completes and a bulk copy takes ~2000 cycles, so depth 4 starved the issuers)
   const uint32_t fixed = (l.n > 0 ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u) + TC_TILES * TN * OUT_LD * 4 +
                          (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4 + (uint32_t)round_up(l.dp4, 4) * 4 +
-                         16 + 40 * 8;
+                         (tp_bias_in_x(l.d) ? 0u : (uint32_t)l.Kp * 4) + 16 + 40 * 8;
   uint32_t nsb = fixed < 227u * 1024u ? (227u * 1024u - fixed) / s.stage : 0u;
   s.nsb = nsb > (uint32_t)TP_NSB_MAX ? (uint32_t)TP_NSB_MAX : nsb;
   uint32_t o = 0;
@@ -53,6 +57,7 @@ __host__ __device__ inline TpSmem tp_smem_layout(const Layout& l, int epi, int k
   s.out = o;   o += TC_TILES * TN * OUT_LD * 4;                       // two staging tiles
   s.state = o; o += (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;
   s.il = o;    o += (uint32_t)round_up(l.dp4, 4) * 4;
+  s.bias = o;  o += tp_bias_in_x(l.d) ? 0u : (uint32_t)l.Kp * 4;       // per-feature bias (d % 8 == 0)
   o = (o + 15) / 16 * 16;
   s.bars = o;  o += 40 * 8;
   s.total = o;
@@ -74,6 +79,7 @@ inline bool tensor_proj_supported(const psbax_paths_t* p) {
   l.dp4 = (p->d <= 2) ? 2 : round_up(p->d, 4);
   l.OS = round_up(l.dp4 + 1, 4);
   l.np_ = lin ? 0 : round_up(p->n, 8);
+  l.Kp = round_up(round_up(p->L, 8) + round_up(p->n, 8), TP_TKB);
   return tp_supported(l);
 }
 // floats appended to the tensor pack: one (hi | lo) Omega_aug image per 32-feature block
@@ -99,7 +105,7 @@ __global__ void k_tensor_proj_pack(Layout lay, float* __restrict__ pack, size_t 
     float x = 0.f;
     if (row < lay.Lp_ft) {  // cos / linear rows: (omega | bias at dp4); kernel rows project to 0
       if (k < lay.d) x = ft[(size_t)row * lay.OS + k];
-      else if (k == lay.d) x = ft[(size_t)row * lay.OS + lay.dp4];
+      else if (k == lay.d && tp_bias_in_x(lay.d)) x = ft[(size_t)row * lay.OS + lay.dp4];
     }
     const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
     om[idx] = split == 0 ? hi : (x - hi);
@@ -126,10 +132,8 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   }
 }
 
-// Warp-level wait for roles with many warps: one converged non-blocking probe by all lanes (the
-// common case: already complete, no divergence); only if that fails does lane 0 poll with
-// backoff while the others park at the reconvergence point (which costs a few hundred cycles).
-__device__ __forceinline__ void mbar_wait_hybrid(uint64_t* bar, uint32_t parity, int lane) {
+// as mbar_wait_hybrid, with a backed-off fallback poll (the producers of this kernel have slack)
+__device__ __forceinline__ void mbar_wait_hybrid_backoff(uint64_t* bar, uint32_t parity, int lane) {
   if (!mbar_test(bar, parity)) {
     if (lane == 0) mbar_wait_backoff(bar, parity);
   }
@@ -182,6 +186,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   const EpiSmem e = epi_carve(sState, EPI, a.k);
 
   for (int i = tid; i < round_up(dp4, 4); i += TC_THREADS) sIl[i] = __ldg(a.pack + lay.off_invls + i);
+  if (lay.n > 0)  // padding dimensions d..dp4-1 of the x tile are read (times inv_ls = 0) but never refilled
+    for (int i = tid; i < TC_TILES * (dp4 - d) * TM; i += TC_THREADS) {
+      const int t = i / ((dp4 - d) * TM), r = i % ((dp4 - d) * TM);
+      sX[(t * dp4 + d) * TM + r] = 0.f;
+    }
+  const bool bias_in_x = tp_bias_in_x(d);
+  float* sBias = reinterpret_cast<float*>(smem + sl.bias);
+  if (!bias_in_x)
+    for (int i = tid; i < lay.Kp; i += TC_THREADS)
+      sBias[i] = i < lay.Lp_ft ? __ldg(a.pack + lay.off_ft + (size_t)i * OS + dp4) : 0.f;
   if (tid == 0) {
     // the producers read the streamed table block, so they release the stage too
     for (int i = 0; i < TP_NSB_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1 + TC_NPROD); }
@@ -214,9 +228,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     const uint32_t obytes = tp_obytes(d), ftbytes = (uint32_t)TP_TKB * OS * 4;
     uint32_t kb = 0, bs = 0, ph = 0;  // block inside the pass; ring stage and its phase
     for (uint32_t it = 0; it < total_blocks; ++it) {
-      const bool has_kernel_rows = (int)(kb + 1) * TP_TKB > lay.Lp_ft;
+      const bool has_kernel_rows = lay.np_ > 0 && (int)(kb + 1) * TP_TKB > lay.Lp_ft;  // (no table slot when np_ == 0)
       TC_TRACE(3, it, 0);
-      mbar_wait_hybrid(&b_empty[bs], ph ^ 1, lane);
+      mbar_wait_hybrid_backoff(&b_empty[bs], ph ^ 1, lane);
       TC_TRACE(3, it, 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&b_full[bs], TP_WBYTES + obytes + (has_kernel_rows ? ftbytes : 0u));
@@ -283,13 +297,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     const uint64_t dW0 = umma_desc_kmajor(smem_u32(sB), 128, C::B_SBO);
     const uint32_t stage16 = STAGE >> 4;
     const uint32_t nkb1 = (uint32_t)nkb - 1;
-    uint32_t kb = 0, pl = 0, bs = 0;
+    uint32_t kb = 0, pl = 0, bs = 0, bph = 0;
     for (uint32_t it = 0; it < total_blocks; ++it) {
       const bool last = kb == nkb1;
       const uint32_t as = it & 1;
       TC_TRACE(0, it, 0);
       if (kb == 0) mbar_wait(d_empty, (pl & 1) ^ 1);
-      mbar_wait(&a_full[as], (it >> 1) & 1);  // (implies b_full: the projection of this block read the stage)
+      mbar_wait(&b_full[bs], bph);  // long complete (the projection of this block read the stage); acquire only
+      mbar_wait(&a_full[as], (it >> 1) & 1);
       __syncwarp();
       tc_fence_after();
       TC_TRACE(0, it, 2);
@@ -314,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       __syncwarp();
       TC_TRACE(0, it, 3);
       if (last) { kb = 0; ++pl; } else ++kb;
-      if (++bs == NSB) bs = 0;
+      if (++bs == NSB) { bs = 0; bph ^= 1; }
     }
   } else if (warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_NPROD) {
     // ================= producers =================
@@ -327,7 +342,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     for (int pass = t0; pass < t1; ++pass) {
       const uint32_t pl = (uint32_t)(pass - t0);
       // ---- X operand of this pass: warp h writes tile (h >> 1), split (h & 1) of its rows ----
-      mbar_wait_hybrid(x_empty, (pl & 1) ^ 1, lane);
+      mbar_wait_hybrid_backoff(x_empty, (pl & 1) ^ 1, lane);
       tc_fence_after();
       {
         const int t = h >> 1, split = h & 1;
@@ -366,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
         const int kbase = kb * TP_TKB + h * 8;
         // ---- arguments of this warp's 8 features x 2 tiles from the projection ----
         if (warp == 0) TC_TRACE(1, it, 0);
-        mbar_wait_hybrid(&z_full[zb], ph, lane);
+        mbar_wait_hybrid_backoff(&z_full[zb], ph, lane);
         tc_fence_after();
         if (warp == 0) TC_TRACE(1, it, 1);
         uint32_t z[TC_TILES][8];
@@ -380,17 +395,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
         float v[TC_TILES][8];
         if (kbase < lay.Lp_ft) {
           const bool lin = kbase >= lay.Lcos;
+          float arg[TC_TILES][8];
 #pragma unroll
           for (int t = 0; t < TC_TILES; ++t)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float arg = __uint_as_float(z[t][j]);
-              v[t][j] = lin ? arg : __cosf(arg);
-            }
+            for (int j = 0; j < 8; ++j) arg[t][j] = __uint_as_float(z[t][j]);
+          if (!bias_in_x) {  // d % 8 == 0: the bias is not part of the projection
+            const float4 b0 = *reinterpret_cast<const float4*>(sBias + kbase);
+            const float4 b1 = *reinterpret_cast<const float4*>(sBias + kbase + 4);
+            const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) arg[t][j] += bj[j];
+          }
+#pragma unroll
+          for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[t][j] = lin ? arg[t][j] : __cosf(arg[t][j]);
+        } else if (kbase >= lay.Lp_ft + lay.np_) {  // padding rows up to the block size (zero weights)
+#pragma unroll
+          for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[t][j] = 0.f;
         } else {  // exact-kernel features: FFMA path (r^2 as a sum of squared differences)
           // the block's table rows sit behind the operand images of the same stage (already
           // landed: the projection MMAs of this block read the stage; the wait returns at once)
-          mbar_wait_hybrid(&b_full[bs], bph, lane);
+          mbar_wait_hybrid_backoff(&b_full[bs], bph, lane);
           const float* ft = reinterpret_cast<const float*>(sB + bs * STAGE + sl.ftk) + (size_t)(h * 8) * OS;
           const float* xr = sX + q * 32 + lane;
           float acc[TC_TILES][8];
@@ -437,7 +468,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
             s2[t][c] = cvt_bf16x2(r1, r0);
           }
         if (warp == 0) TC_TRACE(1, it, 3);
-        mbar_wait_hybrid(&a_empty[as], ph ^ 1, lane);
+        mbar_wait_hybrid_backoff(&a_empty[as], ph ^ 1, lane);
         tc_fence_after();
         if (warp == 0) TC_TRACE(1, it, 4);
 #pragma unroll
@@ -463,7 +494,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     ls.init();
     for (int pass = t0; pass < t1; ++pass) {
       const uint32_t pl = (uint32_t)(pass - t0);
-      mbar_wait_hybrid(d_full, pl & 1, lane);
+      mbar_wait_hybrid_backoff(d_full, pl & 1, lane);
       tc_fence_after();
       const int r = q * 32 + lane;
 #pragma unroll 1

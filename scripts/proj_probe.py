@@ -18,7 +18,7 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-for (S, L, d, n, N) in [(64, 96, 10, 0, 1000), (64, 1000, 10, 122, 5000), (256, 1000, 31, 512, 3001),
+for (S, L, d, n, N) in [(64, 96, 10, 0, 1000), (64, 1000, 10, 122, 5000), (256, 1000, 31, 512, 3001), (256, 1000, 32, 512, 3001), (64, 300, 8, 20, 3001),
                         (70, 200, 5, 9, 100_000)]:
     g = torch.Generator().manual_seed(7)
     X = torch.rand(N, d, generator=g).to(dev)
@@ -35,7 +35,7 @@ for (S, L, d, n, N) in [(64, 96, 10, 0, 1000), (64, 1000, 10, 122, 5000), (256, 
 
 for (name, N, d, S, L, n, op, arg) in [("C5 argmax", 10_000_000, 10, 32, 1000, 122, "argmax", None),
                                        ("C5 top-32", 10_000_000, 10, 64, 1000, 122, "topk", 32),
-                                       ("C3 d=32->31", 149_361, 31, 256, 1000, 512, "topk", 10),
+                                       ("C3 d=32", 149_361, 32, 256, 1000, 512, "topk", 10),
                                        ("d=16 level-set", 4_000_000, 16, 64, 1000, 64, "levelset", 0.0),
                                        ("d=8 level-set", 4_000_000, 8, 64, 1000, 64, "levelset", 0.0),
                                        ("d=5 level-set", 4_000_000, 5, 64, 1000, 64, "levelset", 0.0)]:

@@ -41,7 +41,8 @@ CASES = [
     (20, 40, 5, 7, 1, "linear", 300),           # cos rows + linear rows in one table
     (3, 16, 5, 7, 1, "linear", 200),            # small-S route
     (4, 16, 5, 7, 4, "linear", 200),            # per-sample bases + linear rows
-    (64, 500, 31, 40, 1, "matern52", 1300),     # largest d of the tensor-projection variant
+    (64, 500, 31, 40, 1, "matern52", 1300),     # tensor-projection variant, bias column in the last K slot
+    (64, 200, 24, 30, 1, "rbf", 900),           # projection variant, d % 8 == 0 (bias added by the producers)
     (128, 333, 16, 0, 1, "rbf", 2049),          # projection variant, no kernel term, 2 chunks, ragged
     (40, 64, 7, 200, 1, "matern32", 515),       # projection variant, kernel rows dominate
 ]
@@ -57,7 +58,7 @@ def _tensor_ok(c):
 
 
 def _proj_ok(c):
-    return _tensor_ok(c) and 5 <= c[2] <= 31
+    return _tensor_ok(c) and 5 <= c[2] <= 32
 
 
 ENGINE_CASES = ([(c, "simt") for c in CASES] + [(c, "tensor") for c in CASES if _tensor_ok(c)] +
@@ -348,7 +349,7 @@ def test_randomised_shapes_all_engines():
         engines = ["simt"]
         if G == 1 and S >= 16 and L > 0:
             engines += ["tensor", "tensor_bf16"]
-            if 5 <= d <= 31:
+            if 5 <= d <= 32:
                 engines.append("tensor_proj")
         for eng in engines:
             try:
