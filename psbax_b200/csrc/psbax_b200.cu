@@ -384,23 +384,27 @@ int psbax_subset_select(const float* fx, int64_t ld_fx, const float* etas, int64
   int rc = device_sms(&sms);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // T samples per CTA share every eta load; keep >= ~2 CTAs of 512 threads per SM in flight
-  const int T = (S >= 16 * sms) ? 8 : (S >= 4 * sms) ? 4 : (S >= 2 * sms) ? 2 : 1;
+  // T samples per CTA share every eta load (the L2 -> SM traffic for eta is the second bound after
+  // the ALU work); one CTA of 512 threads per SM, so pick the smallest T that fits S into one wave
+  const int per_sm = (S + sms - 1) / sms;
+  const int T = per_sm > 4 ? 8 : per_sm > 2 ? 4 : per_sm > 1 ? 2 : 1;
   const int threads = (N >= 4096) ? 512 : 256;
-  const size_t smem = (size_t)T * B * 4 + (size_t)T * k * 4 + (size_t)T * 32 * 8;
+  const size_t smem = (size_t)T * ((B + 3) & ~3) * 4 + (size_t)T * k * 4 + (size_t)T * 32 * 8;
   if (smem > 200 * 1024) return fail(PSBAX_E_UNSUPPORTED, "B=%d too large for shared memory", B);
   const int grid = (S + T - 1) / T;
-#define LAUNCH_SS(TT)                                                                           \
+#define LAUNCH_SS2(TT, NN)                                                                      \
   do {                                                                                          \
     if (smem > 48 * 1024)                                                                       \
-      CUDA_TRY(cudaFuncSetAttribute(k_subset_select<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_subset_select<TT><<<grid, threads, smem, st>>>(fx, ld_fx, etas, N, B, S, k, nonneg,          \
-                                                 reinterpret_cast<long long*>(out_idx));        \
+      CUDA_TRY(cudaFuncSetAttribute(k_subset_select<TT, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_subset_select<TT, NN><<<grid, threads, smem, st>>>(fx, ld_fx, etas, N, B, S, k,            \
+                                                     reinterpret_cast<long long*>(out_idx));    \
   } while (0)
+#define LAUNCH_SS(TT) do { if (nonneg) LAUNCH_SS2(TT, true); else LAUNCH_SS2(TT, false); } while (0)
   if (T == 8) LAUNCH_SS(8);
   else if (T == 4) LAUNCH_SS(4);
   else if (T == 2) LAUNCH_SS(2);
   else LAUNCH_SS(1);
+#undef LAUNCH_SS2
 #undef LAUNCH_SS
   CUDA_TRY(cudaGetLastError());
   return PSBAX_OK;

@@ -11,52 +11,156 @@ namespace psbax {
 //   pick 0      = arg max_j mean_b values[b, j]
 //   pick t >= 1 = arg max_j mean_b max(cur[b], values[b, j]), chosen j score 0
 // ---------------------------------------------------------------------------------
-template <int T>
-__global__ void __launch_bounds__(1024) k_subset_select(const float* __restrict__ fx,
-                                                       long long ld_fx,
-                                                       const float* __restrict__ etas,
-                                                       long long N, int B, int S, int k,
-                                                       int nonneg, long long* __restrict__ out_idx) {
+// Register blocking: a thread scores SS_J candidates at once and keeps the running maxima of
+// four noise draws x T samples in registers, so the inner (draw, candidate, sample) step is
+// three ALU instructions (add, max, add) with one eta load per (draw, candidate) and one
+// 16-byte shared-memory load per (four draws, sample).  cur starts at -inf, so the first pick
+// needs no special case; sums run over b in ascending order (same rounding as a scalar loop).
+constexpr int SS_J = 2;
+// packed FP32 (two samples per 64-bit register pair): the two adds of a step become one FADD2 each
+// on the FMA pipe, the max stays scalar on the ALU pipe -> the pipes are balanced at 2 issue
+// cycles per (draw, candidate, sample) instead of 4 on the FMA pipe.  Same IEEE operations.
+__device__ __forceinline__ uint64_t ss_pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void ss_unpack2(uint64_t r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ uint64_t ss_fadd2(uint64_t a, uint64_t b) {
+  uint64_t c;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(c) : "l"(a), "l"(b));
+  return c;
+}
+template <int T, bool NONNEG>
+__global__ void __launch_bounds__(512) k_subset_select(const float* __restrict__ fx,
+                                                      long long ld_fx,
+                                                      const float* __restrict__ etas,
+                                                      long long N, int B, int S, int k,
+                                                      long long* __restrict__ out_idx) {
   extern __shared__ __align__(16) float smem[];
-  float* cur = smem;                                   // [T][B]
-  int* chosen = reinterpret_cast<int*>(cur + T * B);   // [T][k]
+  const int Bp = (B + 3) & ~3;
+  float* cur = smem;                                    // [T][Bp]
+  int* chosen = reinterpret_cast<int*>(cur + T * Bp);   // [T][k]
   float* redv = reinterpret_cast<float*>(chosen + T * k);  // [T][32]
   int* redi = reinterpret_cast<int*>(redv + T * 32);       // [T][32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int sbase = blockIdx.x * T;
   const float invB = 1.0f / (float)B;
+  const int B4 = B & ~3;
+  for (int i = tid; i < T * Bp; i += blockDim.x) cur[i] = -CUDART_INF_F;
+  __syncthreads();
 
   for (int step = 0; step < k; ++step) {
     float bv[T];
     int bi[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) { bv[t] = -CUDART_INF_F; bi[t] = 0x7fffffff; }
-    for (long long j = tid; j < N; j += blockDim.x) {
-      float f[T], acc[T];
+    for (long long j0 = tid; j0 < N; j0 += (long long)SS_J * blockDim.x) {
+      float f[SS_J][T], acc[SS_J][T];
+      long long jr[SS_J];
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const int s = sbase + t;
-        f[t] = (s < S) ? __ldg(fx + j * ld_fx + s) : 0.f;
-        acc[t] = 0.f;
-      }
-      for (int b = 0; b < B; ++b) {
-        const float eta = __ldg(etas + (long long)b * N + j);
+      for (int jj = 0; jj < SS_J; ++jj) {
+        const long long j = j0 + (long long)jj * blockDim.x;
+        jr[jj] = j < N ? j : j0;  // out-of-range slot repeats row j0 (never scored)
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-          float v = f[t] + eta;
-          if (nonneg) v = fmaxf(v, 0.f);
-          if (step > 0) v = fmaxf(v, cur[t * B + b]);
-          acc[t] += v;
+          const int s = sbase + t;
+          f[jj][t] = (s < S) ? __ldg(fx + jr[jj] * ld_fx + s) : 0.f;
+          acc[jj][t] = 0.f;
         }
       }
+      if constexpr (T >= 2) {
+        constexpr int TP = T / 2;
+        uint64_t f2[SS_J][TP], acc2[SS_J][TP];
 #pragma unroll
-      for (int t = 0; t < T; ++t) {
-        float score = acc[t] * invB;
-        if (step > 0) {
-          for (int q = 0; q < step; ++q)
-            if (chosen[t * k + q] == (int)j) score = 0.f;
+        for (int jj = 0; jj < SS_J; ++jj)
+#pragma unroll
+          for (int tp = 0; tp < TP; ++tp) {
+            f2[jj][tp] = ss_pack2(f[jj][2 * tp], f[jj][2 * tp + 1]);
+            acc2[jj][tp] = 0ull;
+          }
+        // the eta values of the next four draws are fetched before this chunk's arithmetic (four
+        // warps per scheduler cannot hide an L2 round trip on their own)
+        float eta_n[4][SS_J];
+        if (B4 > 0) {
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+            for (int jj = 0; jj < SS_J; ++jj) eta_n[bb][jj] = __ldg(etas + (long long)bb * N + jr[jj]);
         }
-        if (better(score, (int)j, bv[t], bi[t])) { bv[t] = score; bi[t] = (int)j; }
+        for (int b0 = 0; b0 < B4; b0 += 4) {
+          float eta_c[4][SS_J];
+          const int bn = (b0 + 4 < B4) ? b0 + 4 : b0;  // last chunk re-reads itself (values unused)
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+            for (int jj = 0; jj < SS_J; ++jj) {
+              eta_c[bb][jj] = eta_n[bb][jj];
+              eta_n[bb][jj] = __ldg(etas + (long long)(bn + bb) * N + jr[jj]);
+            }
+          float c[T][4];
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cur + t * Bp + b0);
+            c[t][0] = c4.x; c[t][1] = c4.y; c[t][2] = c4.z; c[t][3] = c4.w;
+          }
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+            for (int jj = 0; jj < SS_J; ++jj) {
+              const uint64_t eta2 = ss_pack2(eta_c[bb][jj], eta_c[bb][jj]);
+#pragma unroll
+              for (int tp = 0; tp < TP; ++tp) {
+                float lo, hi;
+                ss_unpack2(ss_fadd2(f2[jj][tp], eta2), lo, hi);
+                if (NONNEG) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+                acc2[jj][tp] = ss_fadd2(acc2[jj][tp], ss_pack2(fmaxf(lo, c[2 * tp][bb]), fmaxf(hi, c[2 * tp + 1][bb])));
+              }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < SS_J; ++jj)
+#pragma unroll
+          for (int tp = 0; tp < TP; ++tp) ss_unpack2(acc2[jj][tp], acc[jj][2 * tp], acc[jj][2 * tp + 1]);
+      } else {
+        for (int b0 = 0; b0 < B4; b0 += 4) {
+          const float4 c4 = *reinterpret_cast<const float4*>(cur + b0);
+          const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb)
+#pragma unroll
+            for (int jj = 0; jj < SS_J; ++jj) {
+              float v = f[jj][0] + __ldg(etas + (long long)(b0 + bb) * N + jr[jj]);
+              if (NONNEG) v = fmaxf(v, 0.f);
+              acc[jj][0] += fmaxf(v, c[bb]);
+            }
+        }
+      }
+      for (int b = B4; b < B; ++b)
+#pragma unroll
+        for (int jj = 0; jj < SS_J; ++jj) {
+          const float eta = __ldg(etas + (long long)b * N + jr[jj]);
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            float v = f[jj][t] + eta;
+            if (NONNEG) v = fmaxf(v, 0.f);
+            acc[jj][t] += fmaxf(v, cur[t * Bp + b]);
+          }
+        }
+#pragma unroll
+      for (int jj = 0; jj < SS_J; ++jj) {
+        const long long j = j0 + (long long)jj * blockDim.x;
+        if (j < N) {
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            float score = acc[jj][t] * invB;
+            for (int q = 0; q < step; ++q)
+              if (chosen[t * k + q] == (int)j) score = 0.f;
+            if (better(score, (int)j, bv[t], bi[t])) { bv[t] = score; bi[t] = (int)j; }
+          }
+        }
       }
     }
     // block arg max per sample
@@ -87,8 +191,8 @@ __global__ void __launch_bounds__(1024) k_subset_select(const float* __restrict_
       if (s < S) {
         const int j = chosen[t * k + step];
         float v = __ldg(fx + (long long)j * ld_fx + s) + __ldg(etas + (long long)b * N + j);
-        if (nonneg) v = fmaxf(v, 0.f);
-        cur[idx] = (step > 0) ? fmaxf(cur[idx], v) : v;
+        if (NONNEG) v = fmaxf(v, 0.f);
+        cur[t * Bp + b] = fmaxf(cur[t * Bp + b], v);
       }
     }
     __syncthreads();

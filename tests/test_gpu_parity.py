@@ -231,7 +231,11 @@ def test_grad_matches_oracle():
 
 
 def test_subset_select_matches_oracle():
-    for (S, N, B, k, nonneg) in [(3, 300, 20, 5, False), (40, 500, 16, 10, True), (700, 120, 8, 4, False)]:
+    # (samples, candidates, noise draws, k, nonneg): every samples-per-CTA variant (1, 2, 4, 8), draw counts
+    # that are not multiples of the register block (4), fewer candidates than threads
+    for (S, N, B, k, nonneg) in [(3, 300, 20, 5, False), (40, 500, 16, 10, True), (700, 120, 8, 4, False),
+                                 (3, 300, 13, 5, False), (9, 5, 3, 3, True), (1300, 90, 6, 3, True),
+                                 (300, 64, 5, 2, False), (200, 1100, 7, 3, True)]:
         p = random_params(S, 64, 5, 12, seed=S)
         X = candidates(N, 5)
         g = torch.Generator().manual_seed(2)
