@@ -184,6 +184,21 @@ __device__ __forceinline__ void mbar_wait_hybrid(uint64_t* bar, uint32_t parity,
   }
   __syncwarp();
 }
+// the same with a sleep between the fallback probes, for roles that wait long (the epilogue waits
+// most of a pass for d_full; its polls otherwise take issue slots from the producers)
+template <int NS>
+__device__ __forceinline__ void mbar_wait_hybrid_sleep(uint64_t* bar, uint32_t parity, int lane) {
+  if (!mbar_test(bar, parity)) {
+    if (lane == 0) {
+      uint32_t spins = 0;
+      while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(NS);
+        if (++spins > (1u << 24)) asm volatile("trap;");
+      }
+    }
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -842,7 +857,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     for (int pass = t0; pass < t1; ++pass, ++tl) {
       const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 0);
-      mbar_wait_hybrid(&d_full[buf], dph, lane);
+      mbar_wait_hybrid_sleep<500>(&d_full[buf], dph, lane);
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 1);
       tc_fence_after();
       const int r = q * 32 + lane;

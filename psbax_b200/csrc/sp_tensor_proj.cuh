@@ -124,18 +124,21 @@ inline int tensor_proj_pack(const Layout& l, float* pack, cudaStream_t st) {
 #ifndef TP_BACKOFF
 #define TP_BACKOFF 64
 #endif
+template <int NS = TP_BACKOFF>
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (TP_BACKOFF > 0) __nanosleep(TP_BACKOFF);
+    if (NS > 0) __nanosleep(NS);
     if (++spins > (1u << 24)) asm volatile("trap;");
   }
 }
-
-// as mbar_wait_hybrid, with a backed-off fallback poll (the producers of this kernel have slack)
+// as mbar_wait_hybrid, with a backed-off fallback poll (the producers of this kernel have slack).
+// NS is the sleep between probes: the epilogue waits most of a pass for d_full, and at 64 ns its
+// four pollers were 14 % of all issued instructions of an issue-bound kernel (ncu source view).
+template <int NS = TP_BACKOFF>
 __device__ __forceinline__ void mbar_wait_hybrid_backoff(uint64_t* bar, uint32_t parity, int lane) {
   if (!mbar_test(bar, parity)) {
-    if (lane == 0) mbar_wait_backoff(bar, parity);
+    if (lane == 0) mbar_wait_backoff<NS>(bar, parity);
   }
   __syncwarp();
 }
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     for (uint32_t it = 0; it < total_blocks; ++it) {
       const bool has_kernel_rows = lay.np_ > 0 && (int)(kb + 1) * TP_TKB > lay.Lp_ft;  // (no table slot when np_ == 0)
       TC_TRACE(3, it, 0);
-      mbar_wait_hybrid_backoff(&b_empty[bs], ph ^ 1, lane);
+      mbar_wait_hybrid_backoff<200>(&b_empty[bs], ph ^ 1, lane);
       TC_TRACE(3, it, 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&b_full[bs], TP_WBYTES + obytes + (has_kernel_rows ? ftbytes : 0u));
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     ls.init();
     for (int pass = t0; pass < t1; ++pass) {
       const uint32_t pl = (uint32_t)(pass - t0);
-      mbar_wait_hybrid_backoff(d_full, pl & 1, lane);
+      mbar_wait_hybrid_backoff<500>(d_full, pl & 1, lane);
       tc_fence_after();
       const int r = q * 32 + lane;
 #pragma unroll 1
