@@ -117,6 +117,17 @@ int psbax_workspace_bytes(const psbax_paths_t* paths, int64_t N, int32_t k, size
 int psbax_eval_values(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
                       float* out, int64_t ld_out, void* stream);
 
+/* out[i] = sum_s f_s(X[i, :])^2 (output units): the row-wise squared norm of the path values,
+ * without the [N, S] matrix ever reaching memory.  With the pseudo-paths V = alpha * L^-1
+ * (K + sigma^2 I = L L^T, no RFF part) this is the explained variance k(x,X)(K + sigma^2 I)^-1 k(X,x)
+ * of the exact GP, i.e. the streaming form of the posterior variance that
+ * EntropyAcquisitionFunction.forward needs for q = 1 (src/acquisition_functions/entropy.py:33-41;
+ * SURVEY.md section 8, row f1).  `scratch` (psbax_sumsq_scratch_bytes; 0 bytes when S <= 64) holds
+ * the per-chunk partial sums, added in ascending chunk order (deterministic). */
+int psbax_sumsq_scratch_bytes(const psbax_paths_t* paths, int64_t N, size_t* bytes);
+int psbax_eval_sumsq(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                     float* out, void* scratch, size_t scratch_bytes, void* stream);
+
 /* Fused evaluation + LevelSetEstimator reduction (src/algorithms/levelset.py:34-39)
  * for all S paths: mask bit (i % 32) of mask[s, i / 32] = (f_s(X[i]) > tau);
  * count[s] = popcount; maxval/argmax[s] = max and (smallest) arg max of f_s over

@@ -84,7 +84,7 @@ Layout make_layout(const psbax_paths_t* p) {
     l.Lp = l.Lcos + round_up(p->n, 8);
   }
   l.Sp = round_up(p->S, TN);
-  const bool shared = (p->G == 1) && (p->S >= 16) && (l.Lp > 0);
+  const bool shared = (p->G == 1) && (p->S >= 16) && (l.Lp + l.np_ > 0);
   if (!shared) l.mode = MODE_PERSAMPLE;
   else if (p->engine == PSBAX_ENGINE_TENSOR) l.mode = MODE_TENSOR;
   else if (p->engine == PSBAX_ENGINE_TENSOR_BF16 || p->engine == PSBAX_ENGINE_TENSOR_PROJ ||
@@ -292,6 +292,41 @@ int psbax_eval_values(const psbax_paths_t* paths, const void* pack, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_tensor_mode(pr.a.lay.mode)) return tensor_launch_any(EPI_VALUES, pr.a, pr.sms, st, g_err, sizeof(g_err));
   return dispatch_simt<EPI_VALUES>(pr.a, pr.grid, st);
+}
+
+int psbax_sumsq_scratch_bytes(const psbax_paths_t* paths, int64_t N, size_t* bytes) {
+  int rc = validate(paths);
+  if (rc) return rc;
+  if (!bytes) return fail(PSBAX_E_INVALID, "bytes is NULL");
+  if (N < 1) return fail(PSBAX_E_INVALID, "N must be >= 1");
+  const int chunks = round_up(paths->S, TN) / TN;
+  *bytes = chunks > 1 ? (size_t)chunks * (size_t)N * sizeof(float) : 0;
+  return PSBAX_OK;
+}
+
+int psbax_eval_sumsq(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                     float* out, void* scratch, size_t scratch_bytes, void* stream) {
+  Prepared pr;
+  int rc = prepare(paths, pack, X, N, &pr);
+  if (rc) return rc;
+  if (!out) return fail(PSBAX_E_INVALID, "out is NULL");
+  size_t need = 0;
+  rc = psbax_sumsq_scratch_bytes(paths, N, &need);
+  if (rc) return rc;
+  if (need > 0 && (!scratch || scratch_bytes < need))
+    return fail(PSBAX_E_WORKSPACE, "scratch too small: %zu < %zu bytes", scratch_bytes, need);
+  const int chunks = pr.a.lay.Sp / TN;
+  pr.a.rowsq = chunks > 1 ? static_cast<float*>(scratch) : out;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_tensor_mode(pr.a.lay.mode)) rc = tensor_launch_any(EPI_VALUES, pr.a, pr.sms, st, g_err, sizeof(g_err));
+  else rc = dispatch_simt<EPI_VALUES>(pr.a, pr.grid, st);
+  if (rc) return rc;
+  if (chunks > 1) {
+    k_sumsq_finalize<<<(unsigned)((N + 255) / 256 > 2368 ? 2368 : (N + 255) / 256), 256, 0, st>>>(
+        pr.a.rowsq, chunks, N, out);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return PSBAX_OK;
 }
 
 int psbax_eval_levelset(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,

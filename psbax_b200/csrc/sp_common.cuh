@@ -60,6 +60,8 @@ struct KArgs {
   // VALUES
   float* out;
   long long ld_out;
+  // VALUES, row-norm variant (psbax_eval_sumsq): rowsq[chunk][N] = sum over the chunk's samples of y^2
+  float* rowsq;
   // LEVELSET
   float tau;
   uint32_t* mask;

@@ -95,6 +95,20 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const float* sOut,
   const int warp = tid >> 5, lane = tid & 31;
   const long long N = a.N;
   if constexpr (EPI == EPI_VALUES) {
+    if (a.rowsq != nullptr) {  // sum of squares over this chunk's samples, thread <-> row, ascending s
+      const int ns = min(TN, a.lay.S - s0);
+      for (int r = tid; r < TM; r += NW * 32) {
+        const long long row = (long long)row0 + r;
+        if (row >= N) break;
+        float acc = 0.f;
+        for (int sl = 0; sl < ns; ++sl) {
+          const float y = fmaf(sOut[sl * OUT_LD + r], a.ystd, a.c0);
+          acc = fmaf(y, y, acc);
+        }
+        a.rowsq[(long long)(s0 / TN) * N + row] = acc;
+      }
+      return;
+    }
     // lanes <-> samples so that global stores are contiguous along S
     for (int r = warp; r < TM; r += NW) {
       const long long row = (long long)row0 + r;
@@ -568,6 +582,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_persample(const __grid_constant
 // ---------------------------------------------------------------------------------
 // finalize kernels: reduce the per-CTA partials
 // ---------------------------------------------------------------------------------
+// out[i] = sum over sample chunks (ascending) of part[c][i]
+__global__ void k_sumsq_finalize(const float* __restrict__ part, int chunks, long long N, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < chunks; ++c) acc += part[(long long)c * N + i];
+    out[i] = acc;
+  }
+}
+
 __global__ void k_levelset_finalize(const unsigned int* __restrict__ p_cnt,
                                     const float* __restrict__ p_max,
                                     const int* __restrict__ p_arg, int parts, int Sp, int S,

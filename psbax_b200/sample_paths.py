@@ -151,6 +151,22 @@ class SamplePathBatch:
                                                   self._stream()), "psbax_eval_values")
         return out
 
+    def sumsq(self, X) -> torch.Tensor:
+        """``sum_s f_s(X[i])**2`` for every row: [N] float32 on the GPU (the [N, S] values never reach
+        memory).  With ``posterior_variance_paths`` this is the variance explained by the data."""
+        X = self._x(X)
+        N = X.shape[0]
+        with torch.cuda.device(self.device):
+            out = torch.empty(N, dtype=F32, device=self.device)
+            nbytes = C.c_size_t()
+            _lib.check(self.lib.psbax_sumsq_scratch_bytes(C.byref(self._struct), N, C.byref(nbytes)),
+                       "psbax_sumsq_scratch_bytes")
+            scratch = torch.empty(max(nbytes.value, 4), dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.psbax_eval_sumsq(C.byref(self._struct), self._pack.data_ptr(), X.data_ptr(), N,
+                                                 out.data_ptr(), scratch.data_ptr(), nbytes.value,
+                                                 self._stream()), "psbax_eval_sumsq")
+        return out
+
     def levelset(self, X, threshold: float, want_mask: bool = True, row_offset: int = 0) -> LevelSetResult:
         """Fused evaluation + ``fx > threshold`` for all S paths."""
         X = self._x(X)

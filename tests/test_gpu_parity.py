@@ -45,6 +45,8 @@ CASES = [
     (64, 200, 24, 30, 1, "rbf", 900),           # projection variant, d % 8 == 0 (bias added by the producers)
     (128, 333, 16, 0, 1, "rbf", 2049),          # projection variant, no kernel term, 2 chunks, ragged
     (40, 64, 7, 200, 1, "matern32", 515),       # projection variant, kernel rows dominate
+    (64, 0, 2, 40, 1, "matern52", 1000),        # exact-kernel rows only (posterior-variance pseudo-paths), shared basis
+    (130, 0, 10, 100, 1, "rbf", 700),           # the same, d = 10, three sample chunks
 ]
 
 
@@ -54,7 +56,7 @@ def _tol(p, X=None):
 
 def _tensor_ok(c):
     S, L, d, n, G, kernel, N = c
-    return G == 1 and S >= 16 and (L > 0 or kernel == "linear") and d <= 128
+    return G == 1 and S >= 16 and (L > 0 or n > 0) and d <= 128
 
 
 def _proj_ok(c):
@@ -91,6 +93,18 @@ def test_values(case):
     assert out.shape == ref.shape
     err = np.abs(out - ref).max(axis=0)
     assert (err <= _tol(p, X)).all(), (err / _tol(p, X)).max()
+
+
+def test_sumsq(case):
+    """Row-wise sum of squared path values (psbax_eval_sumsq) against the oracle's value matrix."""
+    p, X, ref, batch = case
+    got = batch.sumsq(X.cuda()).double().cpu().numpy()
+    want = (ref ** 2).sum(axis=1)
+    # |sum (y + e)^2 - sum y^2| <= sum (2 |y| e + e^2) with |e_s| <= tol_s
+    tol = _tol(p, X)
+    bound = (2 * np.abs(ref) * tol[None, :] + tol[None, :] ** 2).sum(axis=1)
+    assert got.shape == want.shape
+    assert (np.abs(got - want) <= bound + 1e-6 * np.abs(want)).all()
 
 
 def test_levelset(case):
@@ -351,7 +365,7 @@ def test_randomised_shapes_all_engines():
         ref = O.eval_paths(p, X.double()).numpy()
         tol = _tol(p)
         engines = ["simt"]
-        if G == 1 and S >= 16 and L > 0:
+        if G == 1 and S >= 16 and (L > 0 or n > 0):
             engines += ["tensor", "tensor_bf16"]
             if 5 <= d <= 32:
                 engines.append("tensor_proj")
