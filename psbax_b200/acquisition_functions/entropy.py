@@ -28,17 +28,49 @@ class EntropyAcquisitionFunction:
 
     __call__ = forward
 
+    def q1_values(self, choices: torch.Tensor) -> torch.Tensor:
+        """``forward(choices.unsqueeze(-2))`` for every row of ``choices`` [m, d] in ONE fused GPU
+        launch (row f1 of SURVEY.md section 8): H = 0.5 log(2 pi) + 0.5 logdet Cov([x, P]) with
+        logdet Cov([x, P]) = logdet Cov(P) + log var(x | P); the conditional variance comes from
+        ``psbax_eval_sumsq`` over pseudo-paths built from the Cholesky factor of the training
+        (+ pending) covariance.  Returns [m] float64 on the choices' device."""
+        from ..sample_paths import posterior_variance
 
-def optimize_acqf_discrete(acq_function, q, choices, max_batch_size=100, unique=True):
-    """Greedy arg max over ``choices`` [m, d]: evaluate in chunks of ``max_batch_size``,
-    take the best row, add it to ``X_pending``, drop it from the choices, repeat q times."""
+        pend = self.X_pending
+        var = posterior_variance(self.model, choices, pending=pend).double().clamp_min(1e-300)
+        val = 0.5 * math.log(2 * math.pi) + 0.5 * torch.log(var)
+        if pend is not None and pend.numel() > 0:
+            covP = self.model.posterior(pend.reshape(1, -1, choices.shape[-1])).covariance_matrix[0]
+            val = val + 0.5 * torch.logdet(covP).to(val.device)
+        return val.to(torch.as_tensor(choices).device)
+
+
+def _fusable(acq_function) -> bool:
+    """The fused path needs the exact-GP stand-in (kernel_matrix / Cholesky access) and a GPU."""
+    model = getattr(acq_function, "model", None)
+    return (hasattr(acq_function, "q1_values") and hasattr(model, "kernel_matrix")
+            and hasattr(model, "y_mean_std") and torch.cuda.is_available())
+
+
+def optimize_acqf_discrete(acq_function, q, choices, max_batch_size=100, unique=True, fused=None):
+    """Greedy arg max over ``choices`` [m, d]: evaluate, take the best row, add it to
+    ``X_pending``, drop it from the choices, repeat q times.  ``fused=None`` uses one fused GPU
+    launch per greedy step (``EntropyAcquisitionFunction.q1_values``) when the model supports it,
+    else the reference's chunks of ``max_batch_size`` through ``acq_function.forward``;
+    ``fused=True`` insists on the GPU path (and raises if it is not available)."""
     choices = torch.as_tensor(choices)
     base_pending = acq_function.X_pending
     remaining = choices
     picked, values = [], []
+    use_fused = _fusable(acq_function) if fused is None else bool(fused)
+    if use_fused and not _fusable(acq_function):
+        raise RuntimeError("fused max-entropy pick needs the psbax_b200 exact-GP model and a CUDA device")
     for _ in range(q):
         with torch.no_grad():
-            vals = torch.cat([acq_function(c.unsqueeze(-2)) for c in remaining.split(max_batch_size)])
+            if use_fused:
+                vals = acq_function.q1_values(remaining)
+            else:
+                vals = torch.cat([acq_function(c.unsqueeze(-2)) for c in remaining.split(max_batch_size)])
         j = int(torch.argmax(vals))
         picked.append(remaining[j])
         values.append(vals[j])

@@ -468,6 +468,61 @@ def posterior_mean_params(model, device=None) -> dict:
                 mean_const=mu, y_mean=y_mean, y_std=y_std)
 
 
+def posterior_variance_params(model, pending: Optional[torch.Tensor] = None, jitter: float = 1e-8,
+                              device=None) -> dict:
+    """Pseudo-paths whose row-wise squared norm is the variance explained by the data
+    (SURVEY.md section 8, row f1):  with K + sigma^2 I = L L^T,
+
+        sum_s f_s(x)^2 = | L^-1 k(X, x) |^2 = k(x, X) (K + sigma^2 I)^-1 k(X, x),
+
+    f_s(x) = sum_i V[s, i] k(x, x_i) / alpha,  V = alpha L^-1  (S = n rows, L = 0 RFF features), so
+    var_post(x) = alpha - sumsq(x) in standardized units.  ``pending`` rows [m, d] are appended as
+    noise-free observations (plus ``jitter``): the variance is then conditional on them, which is
+    what the greedy q > 1 loop of ``optimize_acqf_discrete`` maximises
+    (logdet Cov([x, P]) = logdet Cov(P) + log var(x | P))."""
+    dev = torch.device(device) if device is not None else default_device()
+    X, y, ls, alpha, noise, mu, y_mean, y_std = _model_state(model, dev)
+    n, d = X.shape
+    diag = torch.full((n,), float(noise), dtype=F64, device=dev)
+    if pending is not None and pending.numel() > 0:
+        P = pending.reshape(-1, d).to(dev, F64)
+        X = torch.cat([X, P])
+        diag = torch.cat([diag, torch.full((P.shape[0],), float(jitter) * float(alpha), dtype=F64, device=dev)])
+    from .models.gp import kernel_profile
+
+    a = X / ls
+    K = alpha * kernel_profile(((a[:, None, :] - a[None, :, :]) ** 2).sum(-1), model.kernel) + torch.diag(diag)
+    Lk = torch.linalg.cholesky(K)
+    Linv = torch.linalg.solve_triangular(Lk, torch.eye(X.shape[0], dtype=F64, device=dev), upper=False)
+    S = X.shape[0]
+    return dict(omega=torch.zeros(1, 0, d), bias=torch.zeros(1, 0), W=torch.zeros(S, 0), kernel=model.kernel,
+                Xtrain=X / ls, inv_ls=1.0 / ls, V=alpha * Linv, mean_const=0.0, y_mean=0.0, y_std=1.0)
+
+
+def posterior_variance(model, Xq, pending: Optional[torch.Tensor] = None, device=None,
+                       engine: Optional[str] = None) -> torch.Tensor:
+    """Exact-GP posterior variance (original units, latent f) at every row of ``Xq`` [N, d] in one
+    fused launch: y_std^2 (alpha - sumsq(Xq)).  [N] float32 on the GPU.
+
+    alpha - |L^-1 k|^2 cancels where the data explain most of the prior variance, so the default
+    engine is the 3xTF32 split (measured max abs error 7e-6 alpha against 1.2e-4 alpha for BF16x3
+    at n = 64, noise 1e-4; ``scripts/var_probe.py``) wherever that engine supports the shape."""
+    dev = torch.device(device) if device is not None else default_device()
+    params = posterior_variance_params(model, pending, device=dev)
+    if engine is None:
+        try:
+            batch = SamplePathBatch(**params, device=dev, engine="tensor")
+        except _lib.PsbaxError as ex:  # S < 16 pseudo-paths or operands too large for the TF32 images
+            if "engine needs" not in str(ex):
+                raise
+            batch = SamplePathBatch(**params, device=dev, engine="auto")
+    else:
+        batch = SamplePathBatch(**params, device=dev, engine=engine)
+    alpha = float(model.covar_module.outputscale)
+    _, y_std = model.y_mean_std()
+    return (alpha - batch.sumsq(Xq)) * (float(y_std) ** 2)
+
+
 def dkgp_linear_params(model, S: int, generator: Optional[torch.Generator] = None, device=None) -> dict:
     """DKGP with a linear kernel on the network embedding (``src/utils.py:153-206``): exact
     weight-space draw  Sn^-1 = I / v + E^T E / sigma^2,  mn = Sn E^T (y - mu) / sigma^2,

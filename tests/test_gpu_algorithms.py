@@ -133,6 +133,40 @@ def test_ps_bax_acquisition_end_to_end():
     assert all(tuple(r) in rows for r in x_next.numpy().tolist())
 
 
+@pytest.mark.parametrize("n,d,kernel,noise", [(8, 3, "matern52", 1e-3), (40, 2, "matern52", 1e-4),
+                                              (64, 5, "rbf", 1e-3), (130, 10, "matern32", 1e-2)])
+def test_fused_posterior_variance_and_entropy_pick(n, d, kernel, noise):
+    """Row f1: the max-entropy pick as one fused launch (psbax_eval_sumsq over alpha L^-1 pseudo-paths)
+    against the oracle's exact posterior (float64): variances, q = 1 entropy values, and the greedy
+    q = 3 picks of optimize_acqf_discrete (conditioning on the pending rows)."""
+    from psbax_b200.acquisition_functions import EntropyAcquisitionFunction
+    from psbax_b200.acquisition_functions.entropy import optimize_acqf_discrete
+    from psbax_b200.sample_paths import posterior_variance
+
+    gp = make_gp(n, d, kernel=kernel, noise=noise, seed=n)
+    model = _model_from(gp)
+    g = torch.Generator().manual_seed(5)
+    choices = torch.rand(700, d, dtype=torch.float64, generator=g)
+    ref_var = torch.stack([O.gp_posterior(gp, c[None])[1].reshape(()) for c in choices])
+    scale = float(ref_var.max())
+    var = posterior_variance(model, choices).double().cpu()
+    assert (var - ref_var).abs().max() <= 2e-4 * scale  # 3xTF32 engine where it applies, else BF16x3
+    acq = EntropyAcquisitionFunction(model=model)
+    vals = acq.q1_values(choices)
+    ref_vals = O.entropy_acqf(gp, choices[:, None, :])
+    big = ref_var > 0.05 * scale  # the entropy is only meaningful (and only ever picked) away from the data
+    assert (vals.cpu()[big] - ref_vals[big]).abs().max() <= 5e-3
+    assert int(vals.argmax()) == int(ref_vals.argmax())
+    # greedy q = 3: fused GPU steps == the reference's chunked CPU evaluation == the oracle
+    x_f, v_f = optimize_acqf_discrete(acq, 3, choices, fused=True)
+    x_c, v_c = optimize_acqf_discrete(acq, 3, choices, fused=False)
+    ox, _ = O.optimize_acqf_discrete(gp, choices, 3)
+    assert torch.equal(x_c, ox)
+    assert torch.equal(x_f.cpu(), x_c)
+    assert (v_f.cpu() - v_c).abs().max() <= 5e-3
+    assert acq.X_pending is None
+
+
 def test_lbfgsb_improves_on_raw_samples():
     from psbax_b200.algorithms import LBFGSB
 
