@@ -10,7 +10,7 @@ import math
 import torch
 
 from ..utils import get_function_sample_batch
-from .entropy import EntropyAcquisitionFunction, optimize_acqf_discrete
+from .entropy import EntropyAcquisitionFunction, _fusable, optimize_acqf_discrete
 
 
 def gen_posterior_sampling_batch(model, algorithm, batch_size, **kwargs):
@@ -29,6 +29,17 @@ def gen_posterior_sampling_batch(model, algorithm, batch_size, **kwargs):
         return algorithm.obj_func.get_idx_from_x(x_next)
 
     paths = get_function_sample_batch(model, batch_size, **kwargs)
+    acq_func = EntropyAcquisitionFunction(model=model)
+    if algorithm.params.name == "SimpleLevelSet" and hasattr(algorithm, "pooled_union") and _fusable(acq_func):
+        # The reference pools the coordinate rows of every path's super-level set (S x ~0.45 N rows
+        # with duplicates).  A duplicate of a picked row can never be picked again (singular joint
+        # covariance), so the greedy pick over the de-duplicated union is the same pick: one OR over
+        # the bit masks, then one fused variance launch per greedy step over the union.
+        union = algorithm.pooled_union(paths)
+        x_batch = torch.as_tensor(algorithm.params.x_set)[union]
+        x_next, _ = optimize_acqf_discrete(acq_function=acq_func, q=batch_size, choices=x_batch,
+                                           max_batch_size=100)
+        return x_next
     rows = []
     for x_output in algorithm.execute_batch(paths):
         x_output = torch.as_tensor(x_output)
@@ -36,7 +47,6 @@ def gen_posterior_sampling_batch(model, algorithm, batch_size, **kwargs):
             x_output = x_output.reshape(1, -1)
         rows.append(x_output)
     x_batch = torch.cat(rows)  # pooled outputs of all paths, duplicates kept
-    acq_func = EntropyAcquisitionFunction(model=model)
     x_next, _ = optimize_acqf_discrete(acq_function=acq_func, q=batch_size, choices=x_batch,
                                        max_batch_size=100)
     return x_next

@@ -167,6 +167,29 @@ def test_fused_posterior_variance_and_entropy_pick(n, d, kernel, noise):
     assert acq.X_pending is None
 
 
+def test_ps_bax_levelset_union_pick_equals_reference_pool(monkeypatch):
+    """PS-BAX on a level-set problem: the fused pick over the de-duplicated union of the bit masks ==
+    the reference flow (pool every path's coordinate rows with duplicates, chunks of 100 through the
+    exact posterior on the CPU)."""
+    import psbax_b200.acquisition_functions.posterior_sampling as ps
+    from psbax_b200.algorithms import LevelSetEstimator
+    from psbax_b200.utils import get_mesh, reshape_mesh
+
+    gp = make_gp(12, 2, noise=1e-3, seed=4)
+    model = _model_from(gp)
+    x_set = reshape_mesh(get_mesh(2, 24)).numpy()
+    for thr, q in [(float(np.quantile(gp.train_Y.numpy(), 0.5)), 2), (1e9, 1)]:  # 1e9: empty sets -> arg max rows
+        algo = LevelSetEstimator({"name": "SimpleLevelSet", "threshold": thr, "x_set": x_set})
+        fused = ps.gen_posterior_sampling_batch(model, algo.get_copy(), q, num_rff_features=128,
+                                                generator=torch.Generator(device="cuda").manual_seed(11))
+        with monkeypatch.context() as m:
+            m.setattr(ps, "_fusable", lambda acq: False)
+            pooled = ps.gen_posterior_sampling_batch(model, algo.get_copy(), q, num_rff_features=128,
+                                                     generator=torch.Generator(device="cuda").manual_seed(11))
+        assert fused.shape == (q, 2)
+        assert torch.equal(torch.as_tensor(fused).double().cpu(), torch.as_tensor(pooled).double().cpu())
+
+
 def test_lbfgsb_improves_on_raw_samples():
     from psbax_b200.algorithms import LBFGSB
 
