@@ -78,12 +78,12 @@ class LevelSetEstimator(Algorithm):
             results.append(self._finish(idx.cpu().numpy(), y))
         return results
 
-    def pooled_union(self, paths: SamplePathBatch) -> torch.Tensor:
-        """Row indices (ascending, int64, CPU) of every candidate that belongs to the output of at
-        least one path — the pool ``gen_posterior_sampling_batch`` builds
-        (``posterior_sampling.py:71-78``) without its duplicates and without ever materialising
-        the S x |super-level set| coordinate rows: one fused launch, an OR over the S bit masks,
-        plus the arg max row of every path whose set is empty (``levelset.py:35-37``)."""
+    def pooled_mask(self, paths: SamplePathBatch) -> torch.Tensor:
+        """bool [N] on the GPU: candidate i belongs to the output of at least one path — the pool
+        ``gen_posterior_sampling_batch`` builds (``posterior_sampling.py:71-78``) without its
+        duplicates and without ever materialising the S x |super-level set| coordinate rows: one
+        fused launch, an OR over the S bit masks, plus the arg max row of every path whose set is
+        empty (``levelset.py:35-37``)."""
         X = self.device_candidates(paths.device)
         N = X.shape[0]
         res = paths.levelset(X, self.params.threshold)
@@ -91,11 +91,15 @@ class LevelSetEstimator(Algorithm):
         for s in range(1, paths.S):
             words |= res.mask[s]
         shifts = torch.arange(32, device=words.device, dtype=torch.int32)
-        bits = ((words.unsqueeze(1) >> shifts) & 1).bool().reshape(-1)[:N]
+        bits = ((words.unsqueeze(1) >> shifts) & 1).bool().reshape(-1)[:N].clone()
         empty = res.count == 0
         if bool(empty.any()):
             bits[res.argmax[empty]] = True
-        return bits.nonzero().reshape(-1).cpu()
+        return bits
+
+    def pooled_union(self, paths: SamplePathBatch) -> torch.Tensor:
+        """Row indices (ascending, int64, CPU) of ``pooled_mask``."""
+        return self.pooled_mask(paths).nonzero().reshape(-1).cpu()
 
     def execute(self, f):
         self.run_algorithm_on_f(f)
