@@ -4,10 +4,11 @@
 ``initialize`` / ``run_algorithm_on_f_list`` are on the accelerated path: the reference draws
 ``exe_paths`` (default 30) sample paths one by one and deep-copies the algorithm (including X*) per
 path; here the paths are drawn as one batch and the algorithm runs on all of them in one fused
-GPU launch.  ``forward`` (the expected-information-gain estimate, ``bax_acquisition.py:87-174``) is
-outside the accelerated scope; a plain torch implementation for q = 1
-is provided so that the "bax" policy is usable: H[y(x)] - mean_s H[y(x) | execution path s] with
-exact GP conditioning under fixed hyper-parameters and fixed standardization.
+GPU launch.  ``forward`` (the expected-information-gain estimate, ``bax_acquisition.py:87-174``):
+H[y(X)] - mean_s H[y(X) | execution path s] with exact GP conditioning under fixed hyper-parameters
+and fixed standardization, in plain torch for any q; ``q1_values`` is the same number for every row
+of a candidate matrix through S + 1 fused ``psbax_eval_sumsq`` launches (SURVEY.md section 8f, row
+f3), which ``optimize_acqf_discrete`` uses for its greedy steps.
 """
 import math
 
@@ -84,3 +85,45 @@ class BAXAcquisitionFunction:
         return h_post - h_cond.mean(0)
 
     __call__ = forward
+
+    def q1_values(self, choices: torch.Tensor) -> torch.Tensor:
+        """``forward(choices.unsqueeze(-2))`` for every row of ``choices`` [m, d]: S + 1 fused launches.
+
+        logdet Cov_M([x, P]) = logdet Cov_M(P) + log var_M(x | P) for the current model M_0 and for
+        every fantasy model M_s (data + execution path s, observed with the likelihood noise), P the
+        pending rows (noise-free).  Every conditional variance is one ``psbax_eval_sumsq`` over the
+        pseudo-paths alpha L^-1 of the corresponding augmented training set."""
+        from ..sample_paths import posterior_variance
+
+        choices = torch.as_tensor(choices)
+        d = choices.shape[-1]
+        noise = float(self.model.likelihood.noise.mean())
+        pend = self.X_pending.reshape(-1, d).to(torch.float64) if self.X_pending is not None else None
+        n_pend = 0 if pend is None else pend.shape[0]
+
+        def log_var(extra_x):
+            rows, rnoise = [], []
+            if extra_x is not None and extra_x.numel() > 0:
+                rows.append(extra_x.reshape(-1, d).to(torch.float64))
+                rnoise.append(torch.full((rows[-1].shape[0],), noise, dtype=torch.float64))
+            if n_pend:
+                rows.append(pend)
+                rnoise.append(torch.zeros(n_pend, dtype=torch.float64))
+            if not rows:
+                var = posterior_variance(self.model, choices)
+            else:
+                var = posterior_variance(self.model, choices, pending=torch.cat(rows),
+                                         pending_noise=torch.cat(rnoise))
+            return torch.log(var.double().clamp_min(1e-300))
+
+        val = 0.5 * log_var(None)
+        cond = torch.zeros_like(val)
+        for ep in self.exe_path_list:
+            cond += 0.5 * log_var(torch.as_tensor(np.asarray(ep.x)))
+        val = val - cond / len(self.exe_path_list)
+        if n_pend:  # the terms that do not depend on x
+            P = pend.reshape(1, -1, d)
+            const = self.entropy(self.model.posterior(P).covariance_matrix[0]) - torch.stack(
+                [self.entropy(cm.posterior(P).covariance_matrix[0]) for cm in self.comb_model_list]).mean()
+            val = val + const.to(val.device)
+        return val.to(choices.device)

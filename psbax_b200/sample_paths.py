@@ -469,7 +469,7 @@ def posterior_mean_params(model, device=None) -> dict:
 
 
 def posterior_variance_params(model, pending: Optional[torch.Tensor] = None, jitter: float = 1e-8,
-                              device=None) -> dict:
+                              device=None, pending_noise=None) -> dict:
     """Pseudo-paths whose row-wise squared norm is the variance explained by the data
     (SURVEY.md section 8, row f1):  with K + sigma^2 I = L L^T,
 
@@ -479,7 +479,9 @@ def posterior_variance_params(model, pending: Optional[torch.Tensor] = None, jit
     var_post(x) = alpha - sumsq(x) in standardized units.  ``pending`` rows [m, d] are appended as
     noise-free observations (plus ``jitter``): the variance is then conditional on them, which is
     what the greedy q > 1 loop of ``optimize_acqf_discrete`` maximises
-    (logdet Cov([x, P]) = logdet Cov(P) + log var(x | P))."""
+    (logdet Cov([x, P]) = logdet Cov(P) + log var(x | P)).  ``pending_noise`` (scalar or [m], in
+    standardized units) replaces the jitter: rows observed WITH noise, e.g. the execution path a
+    fantasy model of INFO-BAX is conditioned on (``bax_acquisition.py:177-203``)."""
     dev = torch.device(device) if device is not None else default_device()
     X, y, ls, alpha, noise, mu, y_mean, y_std = _model_state(model, dev)
     n, d = X.shape
@@ -487,7 +489,12 @@ def posterior_variance_params(model, pending: Optional[torch.Tensor] = None, jit
     if pending is not None and pending.numel() > 0:
         P = pending.reshape(-1, d).to(dev, F64)
         X = torch.cat([X, P])
-        diag = torch.cat([diag, torch.full((P.shape[0],), float(jitter) * float(alpha), dtype=F64, device=dev)])
+        if pending_noise is None:
+            extra = torch.full((P.shape[0],), float(jitter) * float(alpha), dtype=F64, device=dev)
+        else:
+            extra = torch.as_tensor(pending_noise, dtype=F64, device=dev).reshape(-1).expand(P.shape[0]).clone()
+            extra = extra.clamp_min(float(jitter) * float(alpha))
+        diag = torch.cat([diag, extra])
     from .models.gp import kernel_profile
 
     a = X / ls
@@ -500,7 +507,7 @@ def posterior_variance_params(model, pending: Optional[torch.Tensor] = None, jit
 
 
 def posterior_variance(model, Xq, pending: Optional[torch.Tensor] = None, device=None,
-                       engine: Optional[str] = None) -> torch.Tensor:
+                       engine: Optional[str] = None, pending_noise=None) -> torch.Tensor:
     """Exact-GP posterior variance (original units, latent f) at every row of ``Xq`` [N, d] in one
     fused launch: y_std^2 (alpha - sumsq(Xq)).  [N] float32 on the GPU.
 
@@ -508,7 +515,7 @@ def posterior_variance(model, Xq, pending: Optional[torch.Tensor] = None, device
     engine is the 3xTF32 split (measured max abs error 7e-6 alpha against 1.2e-4 alpha for BF16x3
     at n = 64, noise 1e-4; ``scripts/var_probe.py``) wherever that engine supports the shape."""
     dev = torch.device(device) if device is not None else default_device()
-    params = posterior_variance_params(model, pending, device=dev)
+    params = posterior_variance_params(model, pending, device=dev, pending_noise=pending_noise)
     if engine is None:
         try:
             batch = SamplePathBatch(**params, device=dev, engine="tensor")

@@ -190,6 +190,30 @@ def test_ps_bax_levelset_union_pick_equals_reference_pool(monkeypatch):
         assert torch.equal(torch.as_tensor(fused).double().cpu(), torch.as_tensor(pooled).double().cpu())
 
 
+def test_info_bax_eig_fused_equals_torch_forward():
+    """Row f3: the INFO-BAX expected information gain for every candidate through S + 1 fused variance
+    launches == the plain float64 forward (current model and S fantasy models conditioned on the
+    execution paths), including the greedy q = 2 pick with a pending row."""
+    from psbax_b200.acquisition_functions import BAXAcquisitionFunction
+    from psbax_b200.acquisition_functions.entropy import optimize_acqf_discrete
+    from psbax_b200.algorithms import TopK
+    from psbax_b200.utils import generate_random_points
+
+    gp = make_gp(10, 3, noise=1e-3, seed=2)
+    model = _model_from(gp)
+    x_path = generate_random_points(150, 3, seed=1234).double()
+    acq = BAXAcquisitionFunction(model, TopK({"x_path": x_path.numpy(), "k": 4}), exe_paths=5)
+    acq.initialize(generator=torch.Generator(device="cuda").manual_seed(1), num_rff_features=128)
+    ref = torch.cat([acq(c.unsqueeze(1)) for c in x_path.split(50)])
+    got = acq.q1_values(x_path).cpu()
+    informative = ref > ref.max() - 3.0  # away from rows whose conditional variance is ~ noise
+    assert (got[informative] - ref[informative]).abs().max() <= 5e-3
+    assert int(got.argmax()) == int(ref.argmax())
+    x_f, _ = optimize_acqf_discrete(acq, 2, x_path, fused=True)
+    x_c, _ = optimize_acqf_discrete(acq, 2, x_path, fused=False)
+    assert torch.equal(x_f.cpu(), x_c)
+
+
 def test_lbfgsb_improves_on_raw_samples():
     from psbax_b200.algorithms import LBFGSB
 
