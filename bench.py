@@ -244,7 +244,7 @@ def run_ours(args):
     words = (N + 31) // 32
 
     def e2e_step():
-        return paths.levelset_streamed(Xh, tau, chunk_rows=1 << 21, row_offset=row_offset)
+        return paths.levelset_streamed(Xh, tau, chunk_rows=int(os.environ.get("PSBAX_E2E_CHUNK", 1 << 21)), row_offset=row_offset)
 
     e2e_step()
     sync_all()
@@ -310,7 +310,7 @@ def run_ours(args):
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, one
                          # ncu --set full capture (profiles/r01_ncu_bench_kernel_bf16x3_details.csv);
                          # algorithmic bytes = 134.2 MB X* + 134.2 MB mask
-                         "traffic": 224.4e6 if eng == "tensor_bf16x3" else None,
+                         "traffic": 224.2e6 if eng == "tensor_bf16x3" else None,
                          "kernel": "fused evaluate+level-set kernel (+3 us finalize)",
                          "kernel_ms": 1e3 * kern_s,
                          "note": (f"algorithmic flops = 2*(L+n)*S per candidate = {2 * (L + NTRAIN) * S}; "
