@@ -789,6 +789,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             for (int t = 0; t < TC_TILES; ++t) kernel_profile8(r2[t], v[t], lay.kernel);
           }
           // split into the two MMA operands
+          if constexpr (BF && !GEN) {
+            // The values of one feature for the thread's two rows already sit in an aligned register
+            // pair (packed projection), so the residual v - bf16(v) is formed per FEATURE over the
+            // (tile 0, tile 1) pair; pairing two features of one row instead cost one MOV per value.
+            static_assert(TC_TILES == 2, "row-pair split");
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {  // column c packs features 2c (low half) and 2c + 1 (high half)
+              const uint32_t p1a = cvt_bf16x2(v[0][2 * c + 1], v[0][2 * c]);
+              const uint32_t p1b = cvt_bf16x2(v[1][2 * c + 1], v[1][2 * c]);
+              const uint64_t ra = ffma2(pack2(__uint_as_float(p1a << 16), __uint_as_float(p1b << 16)),
+                                        pack2(-1.0f, -1.0f), pack2(v[0][2 * c], v[1][2 * c]));
+              const uint64_t rb = ffma2(pack2(__uint_as_float(p1a & 0xffff0000u), __uint_as_float(p1b & 0xffff0000u)),
+                                        pack2(-1.0f, -1.0f), pack2(v[0][2 * c + 1], v[1][2 * c + 1]));
+              float a0, a1, b0, b1;
+              unpack2(ra, a0, a1);
+              unpack2(rb, b0, b1);
+              s1[g][0][c] = p1a;
+              s1[g][1][c] = p1b;
+              s2[g][0][c] = cvt_bf16x2(b0, a0);
+              s2[g][1][c] = cvt_bf16x2(b1, a1);
+            }
+          } else {
 #pragma unroll
           for (int t = 0; t < TC_TILES; ++t) {
             if constexpr (BF) {
@@ -811,6 +833,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
                 s2[g][t][j] = __float_as_uint(v[t][j] - __uint_as_float(hb));
               }
             }
+          }
           }
           if (EARLY ? (g == 0) : (g == NG - 1)) {
             if (tracer) TC_TRACE(1, it, 1);
