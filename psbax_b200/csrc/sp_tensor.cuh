@@ -186,13 +186,29 @@ __device__ __forceinline__ void mbar_wait_hybrid(uint64_t* bar, uint32_t parity,
 }
 // the same with a sleep between the fallback probes, for roles that wait long (the epilogue waits
 // most of a pass for d_full; its polls otherwise take issue slots from the producers)
+// try_wait with an explicit suspend-time hint (ns): the hardware parks the thread until the phase
+// completes or the hint expires, so a long wait costs a handful of instructions instead of a poll
+// every ~45 ns (the default limit; __nanosleep(500) measured no longer than that either)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+#ifndef PSBAX_AEMPTY_HINT
+#define PSBAX_AEMPTY_HINT 0  // measured: 0 (plain try_wait), 300, 1000, 5000 ns all 7.82 ms
+#endif
 template <int NS>
 __device__ __forceinline__ void mbar_wait_hybrid_sleep(uint64_t* bar, uint32_t parity, int lane) {
   if (!mbar_test(bar, parity)) {
     if (lane == 0) {
       uint32_t spins = 0;
-      while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(NS);
+      while (!(NS > 0 ? mbar_try_wait_hint(bar, parity, NS) : mbar_try_wait(bar, parity))) {
         if (++spins > (1u << 24)) asm volatile("trap;");
       }
     }
@@ -837,7 +853,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           }
           if (EARLY ? (g == 0) : (g == NG - 1)) {
             if (tracer) TC_TRACE(1, it, 1);
-            mbar_wait_hybrid(&a_empty[as], aph ^ 1, lane);
+            mbar_wait_hybrid_sleep<PSBAX_AEMPTY_HINT>(&a_empty[as], aph ^ 1, lane);
             if (tracer) TC_TRACE(1, it, 2);
             tc_fence_after();
           }
@@ -880,7 +896,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     for (int pass = t0; pass < t1; ++pass, ++tl) {
       const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 0);
-      mbar_wait_hybrid_sleep<500>(&d_full[buf], dph, lane);
+      mbar_wait_hybrid_sleep<20000>(&d_full[buf], dph, lane);
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 1);
       tc_fence_after();
       const int r = q * 32 + lane;
