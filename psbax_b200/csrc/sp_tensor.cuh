@@ -857,7 +857,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             if (tracer) TC_TRACE(1, it, 2);
             tc_fence_after();
           }
-          if (EARLY || g == NG - 1) {
+          if constexpr (!EARLY && BF && NG == 2) {
+            // the two groups of a warp are adjacent columns: one 8-column store per (tile, split)
+            if (g == NG - 1) {
+#pragma unroll
+              for (int t = 0; t < TC_TILES; ++t) {
+                const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + (h * NG) * C::WCOLS;
+                const uint32_t u1[8] = {s1[0][t][0], s1[0][t][1], s1[0][t][2], s1[0][t][3],
+                                        s1[1][t][0], s1[1][t][1], s1[1][t][2], s1[1][t][3]};
+                const uint32_t u2[8] = {s2[0][t][0], s2[0][t][1], s2[0][t][2], s2[0][t][3],
+                                        s2[1][t][0], s2[1][t][1], s2[1][t][2], s2[1][t][3]};
+                tc_st8(lane_addr + col, u1);
+                tc_st8(lane_addr + col + C::ACT / 2, u2);
+              }
+            }
+          } else if (EARLY || g == NG - 1) {
 #pragma unroll
             for (int gg = EARLY ? g : 0; gg <= g; ++gg)
 #pragma unroll
