@@ -33,6 +33,8 @@
 //                      ACT = 64 (TF32, 2 stages) or 32 (BF16 pairs, 4 stages)
 #pragma once
 #include "sp_common.cuh"
+#include <type_traits>
+
 #include "sp_simt.cuh"
 
 namespace psbax {
@@ -718,13 +720,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         }
         const float* ftb = GEN ? reinterpret_cast<const float*>(sB + bs * STAGE + C::BBYTES) + h * TC_FPW * OS
                                : sFT + kbase0 * OS;
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
+        // PURE: every feature of this warp's slice of the block is a cos feature (the common case):
+        // the same body without the per-group section tests, selects and the kernel-profile branch
+        auto group = [&](auto pure_tag, const int g) {
+          constexpr bool PURE = decltype(pure_tag)::value;
           // 8 features for both tiles' rows: each table row is fetched once and used twice.
           // The RFF / kernel-feature branch is warp-uniform (sections are multiples of 8).
           const int kbase = kbase0 + g * 8;
           const float* ft = ftb + g * 8 * OS;
-          const bool lin = kbase >= lay.Lcos;  // linear-kernel rows: identity activation (warp-uniform)
+          const bool lin = PURE ? false : kbase >= lay.Lcos;  // linear-kernel rows: identity activation (warp-uniform)
           float v[TC_TILES][8];
           if constexpr (GEN) {
             // x from shared memory, 4 dimensions at a time, reused by the 8 features
@@ -774,7 +778,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t) kernel_profile8(acc[t], v[t], lay.kernel);
             }
-          } else if (kbase < lay.Lp_ft) {
+          } else if (PURE || kbase < lay.Lp_ft) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float w[OSC];
@@ -886,6 +890,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
                 }
               }
           }
+        };
+        if (!GEN && kbase0 + TC_FPW <= lay.Lcos) {
+#pragma unroll
+          for (int g = 0; g < NG; ++g) group(std::true_type{}, g);
+        } else {
+#pragma unroll
+          for (int g = 0; g < NG; ++g) group(std::false_type{}, g);
         }
         if constexpr (GEN) {  // done reading the streamed table block
           __syncwarp();
