@@ -181,10 +181,11 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, i
 // and the WARPSYNC slow path of the reconvergence costs a few hundred cycles per wait (ncu source
 // view of the projection kernel: half of the issuer warp's samples sat in those paths).
 __device__ __forceinline__ void mbar_wait_hybrid(uint64_t* bar, uint32_t parity, int lane) {
-  if (!mbar_test(bar, parity)) {
+  // one vote instead of an unconditional reconvergence barrier after a possibly divergent branch
+  if (!__all_sync(0xffffffffu, mbar_test(bar, parity))) {
     if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
   }
-  __syncwarp();
 }
 // the same with a sleep between the fallback probes, for roles that wait long (the epilogue waits
 // most of a pass for d_full; its polls otherwise take issue slots from the producers)
@@ -207,15 +208,15 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 #endif
 template <int NS>
 __device__ __forceinline__ void mbar_wait_hybrid_sleep(uint64_t* bar, uint32_t parity, int lane) {
-  if (!mbar_test(bar, parity)) {
+  if (!__all_sync(0xffffffffu, mbar_test(bar, parity))) {
     if (lane == 0) {
       uint32_t spins = 0;
       while (!(NS > 0 ? mbar_try_wait_hint(bar, parity, NS) : mbar_try_wait(bar, parity))) {
         if (++spins > (1u << 24)) asm volatile("trap;");
       }
     }
+    __syncwarp();
   }
-  __syncwarp();
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(

@@ -65,6 +65,7 @@ __host__ __device__ inline TpSmem tp_smem_layout(const Layout& l, int epi, int k
 }
 // shape rule for the projection variant (BF16x3 engine only)
 __host__ __device__ inline bool tp_supported(const Layout& l) {
+  if (TC_NPROD != 16) return false;  // the kernel assumes four producer warps per lane quarter
   if (l.mode != MODE_TENSOR_BF16 || l.d < TP_MIN_D || l.d > TP_MAX_D) return false;
   const TpSmem sl = tp_smem_layout(l, EPI_TOPK, KMAX);
   return sl.nsb >= (uint32_t)TP_NSB_MIN && sl.total <= TC_SMEM_MAX;
@@ -137,10 +138,10 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
 // four pollers were 14 % of all issued instructions of an issue-bound kernel (ncu source view).
 template <int NS = TP_BACKOFF>
 __device__ __forceinline__ void mbar_wait_hybrid_backoff(uint64_t* bar, uint32_t parity, int lane) {
-  if (!mbar_test(bar, parity)) {
+  if (!__all_sync(0xffffffffu, mbar_test(bar, parity))) {
     if (lane == 0) mbar_wait_backoff<NS>(bar, parity);
+    __syncwarp();
   }
-  __syncwarp();
 }
 
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
@@ -336,7 +337,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     }
   } else if (warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_NPROD) {
     // ================= producers =================
-    static_assert(TC_NPROD == 16, "projection variant: four producer warps per lane quarter");
     const int q = warp & 3, h = (warp - TC_PROD_WARP0) >> 2;  // h: which 8 features; also which X part
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     constexpr int PT = TC_NPROD * 32;
