@@ -59,6 +59,31 @@ class LevelSetResult:
         return torch.nonzero(bits.reshape(-1)[: self.N], as_tuple=False).reshape(-1)
 
 
+def _stream_bounds(N: int, c: int):
+    """Chunk boundaries of the streamed level set: chunks of ``c`` rows (a multiple of 2048) with short
+    chunks (c/8, c/2) at both ends — the first upload and the last download are the only copies
+    that do not overlap with a kernel.  Every boundary but the last is a multiple of 256."""
+    if N < 4 * c:
+        return list(range(0, N, c)) + [N]
+    sizes = [c // 8, c // 2]
+    left = N - sum(sizes)
+    tail = c // 2 + c // 8
+    while left - tail > c:
+        sizes.append(c)
+        left -= c
+    mid = ((left - tail) // 256) * 256
+    if mid > 0:
+        sizes.append(mid)
+        left -= mid
+    sizes.append(c // 2)
+    left -= c // 2
+    sizes.append(left)  # c/8 .. c/8 + 255 rows
+    bounds = [0]
+    for sz in sizes:
+        bounds.append(bounds[-1] + sz)
+    return bounds
+
+
 class SamplePathBatch:
     """S sample paths resident on one GPU."""
 
@@ -199,8 +224,8 @@ class SamplePathBatch:
         if X_host.device.type != "cpu" or X_host.dtype != F32 or X_host.dim() != 2 or X_host.shape[1] != self.d:
             raise PsbaxError("levelset_streamed expects a CPU float32 [N, d] tensor")
         N = X_host.shape[0]
-        chunk_rows = max(4096, (chunk_rows // 256) * 256)
-        bounds = list(range(0, N, chunk_rows)) + [N]
+        chunk_rows = max(4096, (chunk_rows // 2048) * 2048)
+        bounds = _stream_bounds(N, chunk_rows)
         nchunk = len(bounds) - 1
         dev = self.device
         with torch.cuda.device(dev):
@@ -209,14 +234,14 @@ class SamplePathBatch:
                 self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
             s_in, s_out = self._streams
             cache = getattr(self, "_stream_cache", None)
-            if cache is None or cache[0] != (N, chunk_rows):
+            if cache is None or cache[0] != (N, chunk_rows, nchunk):
                 xbuf = [torch.empty(chunk_rows, self.d, dtype=F32, device=dev) for _ in range(2)]
                 masks_h = [torch.empty(self.S, (bounds[c + 1] - bounds[c] + 31) // 32, dtype=torch.int32).pin_memory()
                            for c in range(nchunk)]
                 small = (torch.empty(self.S, dtype=torch.int64).pin_memory(),
                          torch.empty(self.S, dtype=F32).pin_memory(),
                          torch.empty(self.S, dtype=torch.int64).pin_memory())
-                self._stream_cache = ((N, chunk_rows), xbuf, masks_h, small)
+                self._stream_cache = ((N, chunk_rows, nchunk), xbuf, masks_h, small)
             _, xbuf, masks_h, (cnt_h, bv_h, bi_h) = self._stream_cache
             ev_in = [torch.cuda.Event() for _ in range(nchunk)]
             ev_done = [torch.cuda.Event() for _ in range(nchunk)]
