@@ -248,9 +248,6 @@ class SamplePathBatch:
             ev_free = [None, None]  # compute finished with xbuf[b]
             s_in.wait_stream(main)
             s_out.wait_stream(main)
-            tot = torch.zeros(self.S, dtype=torch.int64, device=dev)
-            best_v = torch.full((self.S,), float("-inf"), dtype=F32, device=dev)
-            best_i = torch.full((self.S,), -1, dtype=torch.int64, device=dev)
             results = []
             for c in range(nchunk):
                 lo, hi = bounds[c], bounds[c + 1]
@@ -264,16 +261,17 @@ class SamplePathBatch:
                 r = self.levelset(xbuf[b][: hi - lo], threshold, True, row_offset + lo)
                 ev_free[b] = torch.cuda.Event()
                 ev_free[b].record(main)
-                tot += r.count
-                upd = r.maxval > best_v
-                best_v = torch.where(upd, r.maxval, best_v)
-                best_i = torch.where(upd, r.argmax, best_i)
                 ev_done[c].record(main)
                 results.append(r)  # keeps the device mask alive until its download is queued
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_done[c])
                     masks_h[c].copy_(r.mask, non_blocking=True)
                     r.mask.record_stream(s_out)
+            # combine the per-chunk results once (no small kernels between the chunk launches);
+            # ties go to the earlier chunk, i.e. to the smaller row index
+            tot = torch.stack([r.count for r in results]).sum(0)
+            best_v, which = torch.stack([r.maxval for r in results]).max(0)
+            best_i = torch.stack([r.argmax for r in results]).gather(0, which[None])[0]
             cnt_h.copy_(tot, non_blocking=True)
             bv_h.copy_(best_v, non_blocking=True)
             bi_h.copy_(best_i, non_blocking=True)
