@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           for (int j = 0; j < 8; ++j) {
             const int k = c * 8 + j;
             const float xv = (k < d) ? (ok ? __ldg(xr + k) : 0.f) : (k == d ? 1.0f : 0.f);
-            const uint32_t hb = __float_as_uint(xv) & 0xffffe000u;
+            const uint32_t hb = (__float_as_uint(xv) + 0x1000u) & 0xffffe000u;  // round to TF32: |lo| <= 2^-11 |x|
             v[j] = split == 0 ? hb : __float_as_uint(xv - __uint_as_float(hb));
           }
           tc_st8(lane_addr + TP_COL_X + (t * 2 + split) * 32 + c * 8, v);
