@@ -328,6 +328,19 @@ def test_tensor_engine_many_tiles_matches_simt(engine):
     assert (same_set | ~clear).all()
 
 
+@pytest.mark.parametrize("engine", ["simt", "tensor", "tensor_bf16", "tensor_proj"])
+def test_large_feature_arguments(engine):
+    """Short lengthscales: |omega . x + b| up to a few hundred.  The projection error (fp32 FFMA, or the
+    3xTF32 products of the projection variant) grows with the argument; the contract still holds."""
+    p = random_params(32, 256, 16, 24, seed=77)
+    p.omega = p.omega * 4.0
+    X = candidates(1500, 16)
+    ref = O.eval_paths(p, X.double()).numpy()
+    out = to_batch(p, engine=engine).values(X.cuda()).double().cpu().numpy()
+    err = np.abs(out - ref).max(axis=0)
+    assert (err <= _tol(p, X)).all(), (engine, float((err / _tol(p, X)).max()))
+
+
 def test_levelset_streamed_equals_resident():
     """Host-resident candidates streamed in chunks == one launch over the resident set."""
     p = random_params(64, 200, 2, 16, seed=31)
