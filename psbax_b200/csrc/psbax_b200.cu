@@ -422,7 +422,7 @@ int psbax_subset_select(const float* fx, int64_t ld_fx, const float* etas, int64
   // T samples per CTA share every eta load (the L2 -> SM traffic for eta is the second bound after
   // the ALU work); one CTA of 512 threads per SM, so pick the smallest T that fits S into one wave
   const int per_sm = (S + sms - 1) / sms;
-  const int T = per_sm > 4 ? 8 : per_sm > 2 ? 4 : per_sm > 1 ? 2 : 1;
+  const int T = per_sm > 8 ? 8 : per_sm;  // e.g. S = 1024 on 148 SMs: 147 CTAs of 7 samples, not 128 of 8
   const int threads = (N >= 4096) ? 512 : 256;
   const size_t smem = (size_t)T * ((B + 3) & ~3) * 4 + (size_t)T * k * 4 + (size_t)T * 32 * 8;
   if (smem > 200 * 1024) return fail(PSBAX_E_UNSUPPORTED, "B=%d too large for shared memory", B);
@@ -435,10 +435,16 @@ int psbax_subset_select(const float* fx, int64_t ld_fx, const float* etas, int64
                                                      reinterpret_cast<long long*>(out_idx));    \
   } while (0)
 #define LAUNCH_SS(TT) do { if (nonneg) LAUNCH_SS2(TT, true); else LAUNCH_SS2(TT, false); } while (0)
-  if (T == 8) LAUNCH_SS(8);
-  else if (T == 4) LAUNCH_SS(4);
-  else if (T == 2) LAUNCH_SS(2);
-  else LAUNCH_SS(1);
+  switch (T) {
+    case 8: LAUNCH_SS(8); break;
+    case 7: LAUNCH_SS(7); break;
+    case 6: LAUNCH_SS(6); break;
+    case 5: LAUNCH_SS(5); break;
+    case 4: LAUNCH_SS(4); break;
+    case 3: LAUNCH_SS(3); break;
+    case 2: LAUNCH_SS(2); break;
+    default: LAUNCH_SS(1); break;
+  }
 #undef LAUNCH_SS2
 #undef LAUNCH_SS
   CUDA_TRY(cudaGetLastError());

@@ -118,6 +118,11 @@ __global__ void __launch_bounds__(512) k_subset_select(const float* __restrict__
                 if (NONNEG) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
                 acc2[jj][tp] = ss_fadd2(acc2[jj][tp], ss_pack2(fmaxf(lo, c[2 * tp][bb]), fmaxf(hi, c[2 * tp + 1][bb])));
               }
+              if constexpr (T & 1) {  // odd T: the last sample is not part of a pair
+                float v = f[jj][T - 1] + eta_c[bb][jj];
+                if (NONNEG) v = fmaxf(v, 0.f);
+                acc[jj][T - 1] += fmaxf(v, c[T - 1][bb]);
+              }
             }
         }
 #pragma unroll
