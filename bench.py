@@ -190,6 +190,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -300,7 +301,8 @@ def run_ours(args):
             "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"simt": "f32", "tensor_tf32x3": "f32 (3xTF32 split, fp32 accumulate)",
                                            "tensor_bf16x3": "f32 (BF16x3 split, fp32 accumulate)"}[eng],
-            "data": "synthetic", "config": dict(workload_config(world), engine=eng),
+            "data": "synthetic", "config": dict(workload_config(world), engine=eng,
+                                                **({"numa_node_rank0": numa} if numa is not None else {})),
             "e2e": {"value": evals_step * K / t_e2e_max, "unit": UNIT,
                     "h2d_bytes_per_step": N * D * 4, "d2h_bytes_per_step": S * words * 4 + S * 16,
                     "ms_per_step": 1e3 * t_e2e_max / K},
@@ -337,6 +339,34 @@ def paths_engine(paths):
     if paths.engine == "tensor":
         return "tensor_tf32x3"
     return "tensor_bf16x3"
+
+
+def bind_to_gpu_numa_node(index: int):
+    """Multi-GPU runs: keep this rank's threads (and therefore its pinned staging buffers, placed by
+    first touch) on the NUMA node its GPU hangs off, so that eight ranks streaming 2 x 134 MB per step
+    do not all cross the socket interconnect.  Best effort: returns the node or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:  # nvml prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
 
 
 def main():
