@@ -151,7 +151,7 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
-template <int EPI>
+template <int EPI, bool PAIRX>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_constant__ KArgs a, size_t off_om) {
   using C = TcCfg<true, true>;  // BF16x3 contraction with 32-feature blocks
   extern __shared__ __align__(128) uint8_t tp_smem[];
@@ -190,10 +190,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   const EpiSmem e = epi_carve(sState, EPI, a.k);
 
   for (int i = tid; i < round_up(dp4, 4); i += TC_THREADS) sIl[i] = __ldg(a.pack + lay.off_invls + i);
-  if (lay.n > 0)  // padding dimensions d..dp4-1 of the x tile are read (times inv_ls = 0) but never refilled
+  // x tile of the exact-kernel rows: [i][row] (tile 0, tile 1) pairs for the packed-FP32 path, else
+  // [tile][i][row] for the scalar path.  A template parameter, not a runtime branch: at the
+  // 80-register cap the mere presence of the second path cost the cos path 10 % (spills).
+  constexpr bool pairx = PAIRX;
+  if (lay.n > 0)  // padding dimensions d..dp4-1 are read (times inv_ls = 0) but never refilled
     for (int i = tid; i < TC_TILES * (dp4 - d) * TM; i += TC_THREADS) {
-      const int t = i / ((dp4 - d) * TM), r = i % ((dp4 - d) * TM);
-      sX[(t * dp4 + d) * TM + r] = 0.f;
+      if (pairx) {
+        sX[d * TM * TC_TILES + i] = 0.f;
+      } else {
+        const int t = i / ((dp4 - d) * TM), r = i % ((dp4 - d) * TM);
+        sX[(t * dp4 + d) * TM + r] = 0.f;
+      }
     }
   const bool bias_in_x = tp_bias_in_x(d);
   float* sBias = reinterpret_cast<float*>(smem + sl.bias);
@@ -371,7 +379,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
         const long long lim = a.N * d;
         for (int idx = ptid; idx < TC_TILES * TM * d; idx += PT) {
           const int rr = idx / d, i = idx - rr * d;
-          sX[((rr >> 7) * dp4 + i) * TM + (rr & 127)] = (base + idx < lim) ? __ldg(a.X + base + idx) : 0.f;
+          const float xv = (base + idx < lim) ? __ldg(a.X + base + idx) : 0.f;
+          if (pairx) sX[(i * TM + (rr & 127)) * TC_TILES + (rr >> 7)] = xv;  // one LDS.64 feeds a packed FFMA2
+          else sX[((rr >> 7) * dp4 + i) * TM + (rr & 127)] = xv;
         }
         asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
       }
@@ -426,29 +436,60 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           // landed: the projection MMAs of this block read the stage; the wait returns at once)
           mbar_wait_hybrid_backoff(&b_full[bs], bph, lane);
           const float* ft = reinterpret_cast<const float*>(sB + bs * STAGE + sl.ftk) + (size_t)(h * 8) * OS;
-          const float* xr = sX + q * 32 + lane;
           float acc[TC_TILES][8];
+          if constexpr (PAIRX) {
+            // packed FP32 over the thread's (tile 0, tile 1) rows; inv_ls and the table entry enter as
+            // scalar-broadcast operands:  df = x * inv_ls + (-x_t * inv_ls),  acc += df * df
+            static_assert(TC_TILES == 2, "row-pair arithmetic");
+            const uint64_t* xr = reinterpret_cast<const uint64_t*>(sX) + q * 32 + lane;
+            uint64_t acc2[8];
 #pragma unroll
-          for (int t = 0; t < TC_TILES; ++t)
+            for (int j = 0; j < 8; ++j) acc2[j] = 0ull;
+            for (int i0 = 0; i0 < dp4; i0 += 4) {
+              uint64_t xa[4];
+              float il4[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
-          for (int i0 = 0; i0 < dp4; i0 += 4) {
-            float xa[TC_TILES][4];
+              for (int c = 0; c < 4; ++c) {
+                xa[c] = xr[(i0 + c) * TM];
+                il4[c] = sIl[i0 + c];
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
+                const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const uint64_t df = ffma2(xa[c], pack2(il4[c], il4[c]), pack2(wv4[c], wv4[c]));
+                  acc2[j] = ffma2(df, df, acc2[j]);
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) unpack2(acc2[j], acc[0][j], acc[1][j]);
+          } else {
+            const float* xs = sX + q * 32 + lane;
 #pragma unroll
             for (int t = 0; t < TC_TILES; ++t)
 #pragma unroll
-              for (int c = 0; c < 4; ++c) xa[t][c] = xr[(t * dp4 + i0 + c) * TM] * sIl[i0 + c];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
-              const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
+              for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+            for (int i0 = 0; i0 < dp4; i0 += 4) {
+              float xa[TC_TILES][4];
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const float df = xa[t][c] + wv4[c];
-                  acc[t][j] = fmaf(df, df, acc[t][j]);
-                }
+                for (int c = 0; c < 4; ++c) xa[t][c] = xs[(t * dp4 + i0 + c) * TM] * sIl[i0 + c];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
+                const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    const float df = xa[t][c] + wv4[c];
+                    acc[t][j] = fmaf(df, df, acc[t][j]);
+                  }
+              }
             }
           }
 #pragma unroll
@@ -537,7 +578,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   }
 }
 
-template <int EPI>
+template <int EPI, bool PAIRX>
 int tensor_proj_launch_epi(const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
   const Layout& l = a.lay;
   const int gx = tensor_parts(l, a.N, sms), gy = l.Sp / TN;
@@ -547,9 +588,9 @@ int tensor_proj_launch_epi(const KArgs& a, int sms, cudaStream_t st, char* err, 
     return PSBAX_E_UNSUPPORTED;
   }
   const size_t off_om = l.off_tc + tensor_pack_floats(l);
-  cudaError_t ce = cudaFuncSetAttribute(k_tensor_proj<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
+  cudaError_t ce = cudaFuncSetAttribute(k_tensor_proj<EPI, PAIRX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (ce == cudaSuccess) {
-    k_tensor_proj<EPI><<<dim3(gx, gy), TC_THREADS, sl.total, st>>>(a, off_om);
+    k_tensor_proj<EPI, PAIRX><<<dim3(gx, gy), TC_THREADS, sl.total, st>>>(a, off_om);
     ce = cudaGetLastError();
   }
   if (ce != cudaSuccess) {
@@ -560,9 +601,15 @@ int tensor_proj_launch_epi(const KArgs& a, int sms, cudaStream_t st, char* err, 
 }
 
 inline int tensor_proj_launch(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
-  if (epi == EPI_VALUES) return tensor_proj_launch_epi<EPI_VALUES>(a, sms, st, err, errlen);
-  if (epi == EPI_LEVELSET) return tensor_proj_launch_epi<EPI_LEVELSET>(a, sms, st, err, errlen);
-  return tensor_proj_launch_epi<EPI_TOPK>(a, sms, st, err, errlen);
+  // packed-FP32 exact-kernel rows pay off from d = 13 on (measured: d = 32 -8 %, d = 5 / 10 +6 %)
+  const bool pairx = a.lay.dp4 >= 16 && a.lay.n > 0;
+#define TP_LAUNCH(E)                                                                      \
+  return pairx ? tensor_proj_launch_epi<E, true>(a, sms, st, err, errlen)                 \
+               : tensor_proj_launch_epi<E, false>(a, sms, st, err, errlen)
+  if (epi == EPI_VALUES) TP_LAUNCH(EPI_VALUES);
+  if (epi == EPI_LEVELSET) TP_LAUNCH(EPI_LEVELSET);
+  TP_LAUNCH(EPI_TOPK);
+#undef TP_LAUNCH
 }
 
 inline int tensor_launch_any(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
