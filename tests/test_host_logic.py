@@ -236,3 +236,46 @@ def test_fit_model_boundary():
     m3 = fit_model(X, y, "dkgp", architecture=[8, 4], epochs=5)
     assert isinstance(m3, DKGP) and m3.architecture == [3, 8, 4, 1]
     assert fit_model(X, y, "nope") is None  # every failure returns None, as in the reference
+
+
+def test_stream_chunk_bounds():
+    """Chunking of the streamed level set: full cover, aligned boundaries, short chunks at both ends."""
+    from psbax_b200.sample_paths import _stream_bounds
+
+    for N, c in [(16_777_216, 1 << 21), (50_000, 8192), (4 * 8192, 8192), (4 * 8192 + 1, 8192), (1000, 8192),
+                 (40_000, 8192), (123_457, 4096), (16_777_293, 1 << 21)]:
+        b = _stream_bounds(N, c)
+        sizes = [b[i + 1] - b[i] for i in range(len(b) - 1)]
+        assert b[0] == 0 and b[-1] == N and all(s > 0 for s in sizes)
+        assert all(x % 256 == 0 for x in b[:-1])  # mask words and row tiles stay aligned
+        assert max(sizes) <= c
+        if N >= 4 * c:
+            assert sizes[0] == c // 8 and sizes[-1] < c // 8 + 256
+
+
+def test_posterior_variance_pseudo_paths_on_cpu():
+    """The alpha L^-1 pseudo-paths of the fused max-entropy pick: their squared norm is the variance
+    explained by the data (checked in float64 on the CPU through the oracle's evaluator)."""
+    from psbax_b200.sample_paths import posterior_variance_params
+
+    gp = make_gp(20, 3, noise=1e-3, seed=3)
+    model = SingleTaskGP(gp.train_X, gp.train_Y, kernel=gp.kernel, lengthscale=gp.lengthscale,
+                         outputscale=gp.outputscale, noise=gp.noise, mean_const=gp.mean_const)
+    Xq = torch.rand(50, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    pend = Xq[:2]
+    for pending in (None, pend):
+        kw = posterior_variance_params(model, pending, device="cpu")
+        p = O.PathParams(omega=kw["omega"], bias=kw["bias"], W=kw["W"], kernel=kw["kernel"], Xtrain=kw["Xtrain"],
+                         inv_ls=kw["inv_ls"], V=kw["V"], mean_const=0.0, y_mean=0.0, y_std=1.0)
+        vals = O.eval_paths(p, Xq[2:])  # [N, n (+ m)]
+        y_std = float(model.y_mean_std()[1])
+        var = (float(model.covar_module.outputscale) - (vals ** 2).sum(1)) * y_std ** 2
+        if pending is None:
+            ref = torch.stack([O.gp_posterior(gp, x[None])[1].reshape(()) for x in Xq[2:]])
+        else:  # var(x | P) = Cov([x, P]) Schur complement
+            ref = []
+            for x in Xq[2:]:
+                cov = O.gp_posterior(gp, torch.cat([x[None], pend]))[1]
+                ref.append(cov[0, 0] - cov[0, 1:] @ torch.linalg.solve(cov[1:, 1:], cov[1:, 0]))
+            ref = torch.stack(ref)
+        assert (var - ref).abs().max() <= 1e-6 * float(ref.max()) + 1e-9
