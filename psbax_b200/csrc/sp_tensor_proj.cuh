@@ -1,9 +1,10 @@
-// tcgen05 engine, projection variant (5 <= d <= 31): the feature arguments omega_l . x + b_l are
+// tcgen05 engine, projection variant (5 <= d <= 32): the feature arguments omega_l . x + b_l are
 // themselves computed by the tensor cores, so the producers only do MUFU + the operand split.
 //
 //   Z[256 rows x 32 features] = X_aug[256 x Kx] * Omega_aug^T[Kx x 32]      (3xTF32, fp32 accumulate)
 //       X_aug = (x_0..x_{d-1}, 1, 0..)  hi/lo TF32, written ONCE PER PASS into tensor memory by the
-//               producers (lane = row), A operand of the projection MMAs (TS mode)
+//               producers (lane = row), A operand of the projection MMAs (TS mode); when d % 8 == 0
+//               there is no spare column and the producers add the bias instead
 //       Omega_aug = (omega_l | bias_l | 0..) hi/lo TF32 images streamed by the loader behind the
 //               [W;V] image of the same 32-feature block, B operand
 //   producers: tcgen05.ld their 8 arguments x 2 tiles from Z, cos (or identity for linear-kernel
@@ -11,6 +12,8 @@
 //               BF16x3 split, tcgen05.st into the A stage
 //   contraction and fused reductions as in k_shared_tensor (BF16x3, 32-feature blocks).
 //
+// Warps: 0-15 producers, 16-19 epilogue, 20 contraction issuer, 21 loader, 22 TMEM allocator,
+// 23 projection issuer (it runs up to two blocks ahead of the producers: Z is double-buffered).
 // Tensor-memory columns: D[tile] 0..127 (single-buffered: both tiles are drained to two shared
 // staging tiles before the reduction runs) | X[tile][split] 128..255 | Z[buf][tile] 256..383 |
 // A[stage][tile] 384..511.
