@@ -63,6 +63,13 @@ struct TcCfg {
   static constexpr int B_SBO = TKB * ESZ * 8;            // bytes between 8-row groups
   static constexpr int B_SPLIT2 = 8 * B_SBO;             // rows 64..127
   static constexpr int WCOLS = BF ? 4 : 8;               // A columns per 8 features per split
+  // A-stage column layout of a tile.  Default: [split 1: all features][split 2: all features].
+  // 64-feature BF16x3 blocks: per k-step (= the 16 features of one producer warp) the two splits
+  // sit side by side, [k-step][split][8 columns], so a warp stores its block with ONE 16-column
+  // tcgen05.st per tile.
+  static constexpr bool INTERLEAVED = BF && !GEN;
+  static constexpr int A_KSTEP = INTERLEAVED ? 2 * KCOLS : KCOLS;   // columns between k-steps
+  static constexpr int A_SPLIT2 = INTERLEAVED ? KCOLS : ACT / 2;    // offset of split 2
 };
 __host__ __device__ inline int tc_tkb(bool bf, bool generic) { return (bf && !generic) ? 64 : 32; }
 __host__ __device__ inline uint32_t tc_bbytes(bool bf, bool generic) { return 128u * tc_tkb(bf, generic) * (bf ? 2 : 4); }
@@ -646,7 +653,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             for (int ks = 0; ks < C::KSTEPS; ++ks) {
               const uint64_t b1 = umma_desc_kmajor(bbase + ks * C::B_KSTEP, 128, C::B_SBO);
               const uint64_t b2 = umma_desc_kmajor(bbase + C::B_SPLIT2 + ks * C::B_KSTEP, 128, C::B_SBO);
-              const uint32_t a1 = a_base + t * C::ACT + ks * C::KCOLS, a2 = a1 + C::ACT / 2;
+              const uint32_t a1 = a_base + t * C::ACT + ks * C::A_KSTEP, a2 = a1 + C::A_SPLIT2;
               const uint32_t d = d_addr + t * TN;
               if constexpr (BF) {
                 tc_mma_ts_bf16(d, a1, b1, IDESC, (kb | ks) ? 1u : 0u);
@@ -863,17 +870,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             tc_fence_after();
           }
           if constexpr (!EARLY && BF && NG == 2) {
-            // the two groups of a warp are adjacent columns: one 8-column store per (tile, split)
+            // a warp's 16 features are one k-step: both splits of both groups leave as one 16-column store per tile
             if (g == NG - 1) {
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t) {
-                const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + (h * NG) * C::WCOLS;
-                const uint32_t u1[8] = {s1[0][t][0], s1[0][t][1], s1[0][t][2], s1[0][t][3],
-                                        s1[1][t][0], s1[1][t][1], s1[1][t][2], s1[1][t][3]};
-                const uint32_t u2[8] = {s2[0][t][0], s2[0][t][1], s2[0][t][2], s2[0][t][3],
+                static_assert(C::INTERLEAVED && NG * C::WCOLS == C::KCOLS, "one k-step per producer warp");
+                const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + h * C::A_KSTEP;
+                const uint32_t u[16] = {s1[0][t][0], s1[0][t][1], s1[0][t][2], s1[0][t][3],
+                                        s1[1][t][0], s1[1][t][1], s1[1][t][2], s1[1][t][3],
+                                        s2[0][t][0], s2[0][t][1], s2[0][t][2], s2[0][t][3],
                                         s2[1][t][0], s2[1][t][1], s2[1][t][2], s2[1][t][3]};
-                tc_st8(lane_addr + col, u1);
-                tc_st8(lane_addr + col + C::ACT / 2, u2);
+                tc_st16(lane_addr + col, u);
               }
             }
           } else if (EARLY || g == NG - 1) {
@@ -881,10 +888,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             for (int gg = EARLY ? g : 0; gg <= g; ++gg)
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t) {
-                const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + (h * NG + gg) * C::WCOLS;
+                const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT +
+                                     (C::INTERLEAVED ? h * C::A_KSTEP + gg * C::WCOLS : (h * NG + gg) * C::WCOLS);
                 if constexpr (BF) {
                   tc_st4(lane_addr + col, s1[gg][t]);
-                  tc_st4(lane_addr + col + C::ACT / 2, s2[gg][t]);
+                  tc_st4(lane_addr + col + C::A_SPLIT2, s2[gg][t]);
                 } else {
                   tc_st8(lane_addr + col, s1[gg][t]);
                   tc_st8(lane_addr + col + C::ACT / 2, s2[gg][t]);
