@@ -473,13 +473,13 @@ struct LsRegState {
   }
 };
 
-template <int NW>
-__device__ __forceinline__ void epilogue_levelset_reg(const KArgs& a, const float* sOut, LsRegState<NW>& st,
-                                                      int row0, int s0, int tid) {
+template <int NW, bool FULL>
+__device__ __forceinline__ void epilogue_levelset_reg_impl(const KArgs& a, const float* sOut, LsRegState<NW>& st,
+                                                           int row0, int s0, int tid) {
   constexpr int SPW = TN / NW;
   const int warp = tid >> 5, lane = tid & 31;
   const long long N = a.N;
-  const bool wr = a.mask != nullptr && lane < TM / 32 && (long long)row0 + lane * 32 < N;
+  const bool wr = a.mask != nullptr && lane < TM / 32 && (FULL || (long long)row0 + lane * 32 < N);
 #pragma unroll
   for (int q = 0; q < SPW; ++q) {
     const int sl = warp * SPW + q;
@@ -488,7 +488,7 @@ __device__ __forceinline__ void epilogue_levelset_reg(const KArgs& a, const floa
     for (int g = 0; g < TM / 32; ++g) {
       const int r = g * 32 + lane;
       const int row = row0 + r;
-      const bool valid = row < N;
+      const bool valid = FULL || row < N;  // FULL: every row of the tile exists (all tiles but the last)
       const float y = fmaf(sOut[sl * OUT_LD + r], a.ystd, a.c0);
       const unsigned int word = __ballot_sync(0xffffffffu, valid && (y > a.tau));
       st.cnt[q] += __popc(word);
@@ -498,6 +498,13 @@ __device__ __forceinline__ void epilogue_levelset_reg(const KArgs& a, const floa
     }
     if (wr && s0 + sl < a.lay.S) a.mask[(long long)(s0 + sl) * a.mask_ld + (row0 >> 5) + lane] = mine;
   }
+}
+
+template <int NW>
+__device__ __forceinline__ void epilogue_levelset_reg(const KArgs& a, const float* sOut, LsRegState<NW>& st,
+                                                      int row0, int s0, int tid) {
+  if ((long long)row0 + TM <= a.N) epilogue_levelset_reg_impl<NW, true>(a, sOut, st, row0, s0, tid);
+  else epilogue_levelset_reg_impl<NW, false>(a, sOut, st, row0, s0, tid);
 }
 
 template <int NW>
