@@ -157,21 +157,26 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const float* sOut,
       const int k = a.k;
       float* tv = e.tv + sl * k;
       int* ti = e.ti + sl * k;
+      // the list's last entry is the admission threshold: kept in registers, re-read after insertions
+      float thv = tv[k - 1];
+      int thi = ti[k - 1];
 #pragma unroll 1
       for (int g = 0; g < TM / 32; ++g) {
         const int r = g * 32 + lane;
         const long long row = (long long)row0 + r;
         const float y = fmaf(sOut[sl * OUT_LD + r], a.ystd, a.c0);
-        const float thv = tv[k - 1];
-        const int thi = ti[k - 1];
         const bool pass = (row < N) && better(y, (int)row, thv, thi);
         unsigned int m = __ballot_sync(0xffffffffu, pass);
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const float cv = __shfl_sync(0xffffffffu, y, src);
-          const int ci = __shfl_sync(0xffffffffu, (int)row, src);
-          topk_insert_warp(tv, ti, k, cv, ci, lane);
+        if (m) {
+          do {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const float cv = __shfl_sync(0xffffffffu, y, src);
+            const int ci = __shfl_sync(0xffffffffu, (int)row, src);
+            topk_insert_warp(tv, ti, k, cv, ci, lane);
+          } while (m);
+          thv = tv[k - 1];
+          thi = ti[k - 1];
         }
       }
     }
