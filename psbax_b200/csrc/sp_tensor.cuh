@@ -401,7 +401,9 @@ inline bool tensor_supported(const psbax_paths_t* p, bool bf16) {
 inline int tensor_parts(const Layout& l, long long N, int sms) {
   const long long nt = (N + TC_TILES * TM - 1) / (TC_TILES * TM);  // passes of 256 rows
   const int gy = l.Sp / TN;
-  long long gx = (sms + gy - 1) / gy;
+  // one CTA per SM and ONE wave: gx * gy <= #SM (rounding up put 160 CTAs on 148 SMs for 16 sample
+  // chunks: a second wave of 12 CTAs doubled the time)
+  long long gx = sms / gy;
   if (gx > nt) gx = nt;
   if (gx < 1) gx = 1;
   return (int)gx;
