@@ -123,7 +123,7 @@ void grid_for(const Layout& l, long long N, int sms, int* gx, int* gy, int* ntil
   const long long nt = (N + TM - 1) / TM;
   *ntiles = (int)nt;
   *gy = l.Sp / TN;
-  long long want = (2LL * sms + *gy - 1) / *gy;
+  long long want = (2LL * sms) / *gy;  // two CTAs per SM, one wave
   if (want < 1) want = 1;
   long long g = nt < want ? nt : want;
   if (g < 1) g = 1;
