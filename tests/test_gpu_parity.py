@@ -341,6 +341,25 @@ def test_large_feature_arguments(engine):
     assert (err <= _tol(p, X)).all(), (engine, float((err / _tol(p, X)).max()))
 
 
+@pytest.mark.parametrize("engine,d", [("simt", 2), ("tensor", 2), ("tensor_bf16", 2), ("tensor_bf16", 40), ("tensor_proj", 10)])
+def test_single_candidate(engine, d):
+    """N = 1: one valid row in the first tile of the only pass."""
+    p = random_params(64, 100, d, 20, seed=9)
+    X = candidates(1, d)
+    ref = O.eval_paths(p, X.double()).numpy()  # [1, S]
+    b = to_batch(p, engine=engine)
+    tol = _tol(p, X)
+    assert (np.abs(b.values(X.cuda()).double().cpu().numpy() - ref) <= tol[None, :]).all()
+    res = b.levelset(X.cuda(), float(np.median(ref)))
+    mask = unpack_mask(res.mask, 1)
+    decided = np.abs(ref[0] - np.median(ref)) > tol
+    assert (mask[:, 0][decided] == (ref[0] > np.median(ref))[decided]).all()
+    assert (res.argmax.cpu().numpy() == 0).all()
+    val, idx = b.topk(X.cuda(), 1)
+    assert (idx.cpu().numpy() == 0).all() and (np.abs(val[:, 0].double().cpu().numpy() - ref[0]) <= tol).all()
+    assert np.abs(b.sumsq(X.cuda()).double().cpu().numpy()[0] - (ref[0] ** 2).sum()) <= (2 * np.abs(ref[0]) * tol + tol ** 2).sum() + 1e-6
+
+
 def test_levelset_streamed_equals_resident():
     """Host-resident candidates streamed in chunks == one launch over the resident set."""
     p = random_params(64, 200, 2, 16, seed=31)
