@@ -48,8 +48,9 @@ class EntropyAcquisitionFunction:
 def _fusable(acq_function) -> bool:
     """The fused path needs the exact-GP stand-in (kernel_matrix / Cholesky access) and a GPU."""
     model = getattr(acq_function, "model", None)
-    return (hasattr(acq_function, "q1_values") and hasattr(model, "kernel_matrix")
-            and hasattr(model, "y_mean_std") and torch.cuda.is_available())
+    exact_gp = hasattr(model, "kernel_matrix") and hasattr(model, "y_mean_std")
+    deep_kernel = getattr(model, "dkl", False) and hasattr(model, "weight_posterior")
+    return hasattr(acq_function, "q1_values") and (exact_gp or deep_kernel) and torch.cuda.is_available()
 
 
 def optimize_acqf_discrete(acq_function, q, choices, max_batch_size=100, unique=True, fused=None):

@@ -54,6 +54,35 @@ class DKGP:
         p = next(net.parameters())
         return net(X.to(p.device, p.dtype))
 
+    def weight_posterior(self, pending=None, jitter: float = 1e-8):
+        """Weight-space posterior of the linear-kernel GP on the embedding (``src/utils.py:153-182``):
+        Sn^-1 = I / v + E^T E / sigma^2, mn = Sn E^T (y - mu) / sigma^2.  ``pending`` rows [m, d_in] are
+        added as noise-free observations (variance ``jitter * v``), which only changes Sn.
+        Returns (mn [h], Sn [h, h]) in float64 on the network's device."""
+        with torch.no_grad():
+            E = self.embedding(self.train_inputs[0]).to(DT)
+            h = E.shape[1]
+            v = float(self.covar_module.base_kernel.variance)
+            sigma2 = float(self.likelihood.noise.reshape(-1)[0])
+            mu = float(self.mean_module.constant)
+            prec = torch.eye(h, dtype=DT, device=E.device) / v + E.T @ E / sigma2
+            mn = torch.linalg.solve(prec, E.T @ (self.train_targets.to(E.device) - mu)) / sigma2
+            if pending is not None and pending.numel() > 0:
+                Ep = self.embedding(pending.reshape(-1, self.train_inputs[0].shape[1])).to(DT)
+                prec = prec + Ep.T @ Ep / (jitter * v)
+            return mn, torch.linalg.inv(prec)
+
+    def posterior(self, X):
+        """Latent posterior at X [..., q, d_in]: mean e(X) mn + mu, covariance e(X) Sn e(X)^T
+        (what the exact GP with kernel v <e, e'> gives; no outcome transform, as in the reference)."""
+        from .gp import Posterior
+
+        mn, Sn = self.weight_posterior()
+        with torch.no_grad():
+            E = self.embedding(X.reshape(-1, X.shape[-1])).to(DT).reshape(*X.shape[:-1], -1)
+        mean = E @ mn + float(self.mean_module.constant)
+        return Posterior(mean, E @ Sn @ E.transpose(-1, -2))
+
     def train_model(self, X, Y, lr=1e-2, num_iter=100):
         """Adam on the negative exact MLL of y ~ N(mu, v E E^T + sigma^2 I) over the network weights,
         log v, log(sigma^2 - 1e-4) and mu."""

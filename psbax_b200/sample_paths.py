@@ -538,6 +538,8 @@ def posterior_variance(model, Xq, pending: Optional[torch.Tensor] = None, device
     engine is the 3xTF32 split (measured max abs error 7e-6 alpha against 1.2e-4 alpha for BF16x3
     at n = 64, noise 1e-4; ``scripts/var_probe.py``) wherever that engine supports the shape."""
     dev = torch.device(device) if device is not None else default_device()
+    if getattr(model, "dkl", False):
+        return _dkgp_posterior_variance(model, Xq, pending, dev, engine)
     params = posterior_variance_params(model, pending, device=dev, pending_noise=pending_noise)
     if engine is None:
         try:
@@ -551,6 +553,26 @@ def posterior_variance(model, Xq, pending: Optional[torch.Tensor] = None, device
     alpha = float(model.covar_module.outputscale)
     _, y_std = model.y_mean_std()
     return (alpha - batch.sumsq(Xq)) * (float(y_std) ** 2)
+
+
+def _dkgp_posterior_variance(model, Xq, pending, dev, engine) -> torch.Tensor:
+    """Deep-kernel GP (linear kernel on the embedding): var(x) = e(x)^T Sn e(x) = |Ls^T e(x)|^2 with
+    Sn = Ls Ls^T the weight-space posterior covariance (conditioned on the pending rows): h linear-
+    kernel pseudo-paths V = Ls^T over the embedded candidates — ``psbax_eval_sumsq`` gives the
+    variance directly."""
+    net = model.feature_extractor.to(dev)
+    _, Sn = model.weight_posterior(pending.to(dev) if pending is not None else None)
+    Ls = torch.linalg.cholesky(Sn.to(dev))
+    h = Ls.shape[0]
+
+    def embed(X):
+        return net(X.to(dev, next(net.parameters()).dtype)).to(F32)
+
+    batch = SamplePathBatch(omega=torch.zeros(1, 0, h), bias=torch.zeros(1, 0), W=torch.zeros(h, 0), kernel="linear",
+                            Xtrain=torch.eye(h, dtype=F64), inv_ls=torch.ones(h, dtype=F64), V=Ls.T.contiguous(),
+                            mean_const=0.0, y_mean=0.0, y_std=1.0, device=dev, engine=engine or "auto",
+                            input_transform=embed)
+    return batch.sumsq(Xq)
 
 
 def dkgp_linear_params(model, S: int, generator: Optional[torch.Generator] = None, device=None) -> dict:

@@ -276,6 +276,45 @@ def test_dkgp_linear_paths_topk():
     assert (f(cand[:7].unsqueeze(1)) - ref[:7, 3]).abs().max() <= tol[3]
 
 
+def test_dkgp_ps_bax_pick_fused_equals_torch(monkeypatch):
+    """C3 flow (DKGP + TopK + posterior sampling): the max-entropy pick over the pooled top-k rows with the
+    deep-kernel variance e(x)^T Sn e(x) as one fused launch == the float64 torch posterior, greedy q = 3."""
+    import psbax_b200.acquisition_functions.posterior_sampling as ps
+    from psbax_b200.acquisition_functions import EntropyAcquisitionFunction
+    from psbax_b200.algorithms import TopK
+    from psbax_b200.models import DKGP
+
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(3)
+    X = torch.rand(40, 12, dtype=torch.float64, generator=g)
+    y = torch.sin(X.sum(-1))
+    y = (y - y.mean()) / y.std()
+    model = DKGP(X, y, architecture=[12, 16, 8, 1])
+    model.train_model(X, y, lr=1e-2, num_iter=20)
+    cand = torch.rand(400, 12, dtype=torch.float64, generator=g)
+    # weight-space posterior == exact GP with kernel v <e, e'> on the embedding (float64)
+    with torch.no_grad():
+        E, Eq = model.embedding(X).double().cpu(), model.embedding(cand[:5]).double().cpu()
+    v, s2 = float(model.covar_module.base_kernel.variance), float(model.likelihood.noise[0])
+    Kinv = torch.linalg.inv(v * E @ E.T + s2 * torch.eye(40, dtype=torch.float64))
+    cov_ref = v * Eq @ Eq.T - v * Eq @ E.T @ Kinv @ E @ Eq.T * v
+    assert (model.posterior(cand[:5]).covariance_matrix.cpu() - cov_ref).abs().max() <= 1e-8
+    acq = EntropyAcquisitionFunction(model=model)
+    ref = torch.cat([acq(c.unsqueeze(1)) for c in cand.split(100)]).cpu()
+    got = acq.q1_values(cand).cpu()
+    assert (got - ref).abs().max() <= 2e-3 and int(got.argmax()) == int(ref.argmax())
+    algo = TopK({"x_path": cand.numpy(), "k": 5})
+    fused = ps.gen_posterior_sampling_batch(model, algo.get_copy(), 3,
+                                            generator=torch.Generator(device="cuda").manual_seed(11))
+    with monkeypatch.context() as m:
+        import psbax_b200.acquisition_functions.entropy as ent
+
+        m.setattr(ent, "_fusable", lambda acq_function: False)
+        plain = ps.gen_posterior_sampling_batch(model, algo.get_copy(), 3,
+                                                generator=torch.Generator(device="cuda").manual_seed(11))
+    assert fused.shape == (3, 12) and torch.equal(fused.double().cpu(), plain.double().cpu())
+
+
 def test_info_bax_initialize_runs_the_batch_path():
     """BAXAcquisitionFunction.initialize / run_algorithm_on_f_list (bax_acquisition.py:221-277):
     exe_paths sample paths in one fused launch; the EIG of a q = 1 candidate is finite and the
