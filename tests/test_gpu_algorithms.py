@@ -117,6 +117,44 @@ def test_subset_select_algorithm_on_paths():
         assert exe_path.idxes == oidx or abs(score(exe_path.idxes) - score(oidx)) < 1e-5
 
 
+def test_ps_bax_subset_select_branch():
+    """``gen_posterior_sampling_batch`` with SubsetSelect (``posterior_sampling.py:49-64``): ceil(batch / k)
+    paths, their selected labels pooled, max-entropy pick over the pooled rows, labels returned."""
+    from psbax_b200.acquisition_functions import gen_posterior_sampling_batch
+    from psbax_b200.algorithms import SubsetSelect
+
+    N, B, k = 300, 10, 4
+    gp = make_gp(10, 5, noise=1e-3, seed=6)
+    model = _model_from(gp)
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(N, 5, generator=g, dtype=torch.float64)
+    etas = 0.5 * torch.randn(B, N, generator=g, dtype=torch.float64).numpy()
+    labels = [f"gene{i}" for i in range(N)]
+
+    class Obj:
+        noise_type, nonneg = "additive", False
+        df = types.SimpleNamespace(index=labels)
+
+        def __init__(self):
+            self.etas = etas
+            self.x_to_idx = {tuple(r.tolist()): labels[i] for i, r in enumerate(x)}
+
+        def get_x(self, idx=None):
+            return x if idx is None else x[[labels.index(i) for i in idx]]
+
+        def get_noisy_f_lst(self, fx):
+            return fx.squeeze() + self.etas
+
+        def get_idx_from_x(self, X):
+            return [self.x_to_idx[tuple(r.tolist())] for r in X]
+
+    algo = SubsetSelect({"k": k})
+    algo.set_obj_func(Obj())
+    picked = gen_posterior_sampling_batch(model, algo, 6, generator=torch.Generator(device="cuda").manual_seed(2),
+                                          num_rff_features=128)
+    assert len(picked) == 6 and len(set(picked)) == 6 and all(lbl in labels for lbl in picked)
+
+
 def test_ps_bax_acquisition_end_to_end():
     from psbax_b200.acquisition_functions import gen_posterior_sampling_batch
     from psbax_b200.algorithms import TopK
