@@ -697,7 +697,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
       static_assert(TC_TILES == 2, "the packed-FMA producers pair the two row tiles of a pass");
       uint64_t xp[GEN ? 1 : DP];  // (x of tile 0, x of tile 1) per dimension
       if constexpr (GEN) {
-        // stage the pass's 256 rows transposed: sX[tile][i][row]; producer-only named barrier
+        // stage the pass's 256 rows transposed as (tile 0, tile 1) pairs: sX[i][row][tile], so that one
+        // LDS.64 feeds a packed FFMA2 over the thread's two rows; producer-only named barrier
         constexpr int PT = TC_NPROD * 32;
         const int ptid = tid - TC_PROD_WARP0 * 32;
         asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");  // everyone done with the previous tile
@@ -705,12 +706,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         const long long lim = a.N * lay.d;
         for (int idx = ptid; idx < TC_TILES * TM * lay.d; idx += PT) {
           const int rr = idx / lay.d, i = idx - rr * lay.d;  // rr in [0, 256)
-          sX[((rr >> 7) * lay.dp4 + i) * TM + (rr & 127)] = (base + idx < lim) ? __ldg(a.X + base + idx) : 0.f;
+          sX[(i * TM + (rr & 127)) * TC_TILES + (rr >> 7)] = (base + idx < lim) ? __ldg(a.X + base + idx) : 0.f;
         }
-        for (int idx = ptid; idx < TC_TILES * TM * (lay.dp4 - lay.d); idx += PT) {
-          const int rr = idx % (TC_TILES * TM), i = lay.d + idx / (TC_TILES * TM);
-          sX[((rr >> 7) * lay.dp4 + i) * TM + (rr & 127)] = 0.f;
-        }
+        for (int idx = ptid; idx < TC_TILES * TM * (lay.dp4 - lay.d); idx += PT)
+          sX[lay.d * TM * TC_TILES + idx] = 0.f;
         asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
       } else {
         const long long row0 = (long long)pass * TC_TILES * TM + q * 32 + lane, row1 = row0 + TM;
@@ -748,44 +747,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           const bool lin = PURE ? false : kbase >= lay.Lcos;  // linear-kernel rows: identity activation (warp-uniform)
           float v[TC_TILES][8];
           if constexpr (GEN) {
-            // x from shared memory, 4 dimensions at a time, reused by the 8 features
+            // x pairs from shared memory, 4 dimensions at a time, reused by the 8 features; packed FP32
+            // over the thread's two rows with the table entry (and inv_ls) as scalar-broadcast operands
             const bool rff = kbase < lay.Lp_ft;
-            float acc[TC_TILES][8];
+            uint64_t acc2[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float b0 = rff ? ft[j * OS + lay.dp4] : 0.f;
-#pragma unroll
-              for (int t = 0; t < TC_TILES; ++t) acc[t][j] = b0;
+              acc2[j] = pack2(b0, b0);
             }
-            const float* xr = sX + q * 32 + lane;
+            const uint64_t* xr = reinterpret_cast<const uint64_t*>(sX) + q * 32 + lane;
             for (int i0 = 0; i0 < lay.dp4; i0 += 4) {
-              float xa[TC_TILES][4];
+              uint64_t xa[4];
 #pragma unroll
-              for (int t = 0; t < TC_TILES; ++t)
+              for (int c = 0; c < 4; ++c) xa[c] = xr[(i0 + c) * TM];
+              if (rff) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  xa[t][c] = xr[(t * lay.dp4 + i0 + c) * TM];
-                  if (!rff) xa[t][c] *= sIl[i0 + c];
+                for (int j = 0; j < 8; ++j) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
+                  const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) acc2[j] = ffma2(xa[c], pack2(wv4[c], wv4[c]), acc2[j]);
                 }
+              } else {
+                float il4[4];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
-                const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
+                for (int c = 0; c < 4; ++c) il4[c] = sIl[i0 + c];
 #pragma unroll
-                for (int t = 0; t < TC_TILES; ++t)
+                for (int j = 0; j < 8; ++j) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
+                  const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                   for (int c = 0; c < 4; ++c) {
-                    if (rff) {
-                      acc[t][j] = fmaf(xa[t][c], wv4[c], acc[t][j]);
-                    } else {
-                      const float df = xa[t][c] + wv4[c];
-                      acc[t][j] = fmaf(df, df, acc[t][j]);
-                    }
+                    const uint64_t df = ffma2(xa[c], pack2(il4[c], il4[c]), pack2(wv4[c], wv4[c]));
+                    acc2[j] = ffma2(df, df, acc2[j]);
                   }
+                }
               }
             }
-            // (scalar FMAs on purpose: packing x pairs loaded from shared memory costs more MOVs
-            // than the packed FMA saves — measured 4.4 -> 5.5 ms at d = 32)
+            float acc[TC_TILES][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) unpack2(acc2[j], acc[0][j], acc[1][j]);
             if (rff) {
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t)
