@@ -356,7 +356,7 @@ __host__ __device__ inline TcSmem tc_smem_layout_impl(const Layout& l, int epi, 
   uint32_t o = 0;
   s.b = o;     o += s.nsb * s.stage;
   s.ft = o;    o += generic ? 0u : kp * l.OS * 4;                         // resident table (small d)
-  s.x = o;     o += generic ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u;   // x tile [tile][i][row]
+  s.x = o;     o += generic ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u;   // x tile [i][row] of (tile 0, tile 1) pairs
   s.out = o;   o += TN * OUT_LD * 4;
   s.state = o; o += (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;
   s.il = o;    o += (uint32_t)round_up(l.dp4, 4) * 4;
