@@ -604,8 +604,11 @@ int tensor_proj_launch_epi(const KArgs& a, int sms, cudaStream_t st, char* err, 
 }
 
 inline int tensor_proj_launch(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
-  // packed-FP32 exact-kernel rows pay off from d = 13 on (measured: d = 32 -8 %, d = 5 / 10 +6 %)
-  const bool pairx = a.lay.dp4 >= 16 && a.lay.n > 0;
+  // Packed-FP32 exact-kernel rows: measured per instantiation (same box, d = 5 / 10 / 32).  The
+  // level-set kernel (register-resident epilogue state, tightest register budget) only gains from
+  // d = 13 on (d = 10: 7.78 -> 8.23 ms, d = 32: 3.01 -> 2.87); top-k and values gain from d = 5
+  // (C5 top-32 8.65 -> 8.48 ms).
+  const bool pairx = a.lay.n > 0 && a.lay.dp4 >= (epi == EPI_LEVELSET ? 16 : 8);
 #define TP_LAUNCH(E)                                                                      \
   return pairx ? tensor_proj_launch_epi<E, true>(a, sms, st, err, errlen)                 \
                : tensor_proj_launch_epi<E, false>(a, sms, st, err, errlen)
