@@ -56,7 +56,7 @@ enum { /* psbax_paths_t.kernel */
 };
 
 enum { /* psbax_paths_t.engine: which kernel family evaluates a shared basis.  AUTO picks
-        * TENSOR_BF16 when the shape allows (G == 1, S >= 16, L > 0, d <= 16), else SIMT. */
+        * the tensor engines when the basis is shared (G == 1) and S >= 2 or d >= 5, else the FFMA / MUFU kernels. */
   PSBAX_ENGINE_AUTO = 0,
   PSBAX_ENGINE_SIMT = 1,   /* FFMA + MUFU kernels */
   PSBAX_ENGINE_TENSOR = 2,      /* tcgen05 kernel, 3xTF32 operand split (G == 1 only) */

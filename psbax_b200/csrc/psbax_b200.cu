@@ -59,11 +59,11 @@ int validate(const psbax_paths_t* p) {
   if ((p->engine == PSBAX_ENGINE_TENSOR && !tensor_supported(p, false)) ||
       (p->engine == PSBAX_ENGINE_TENSOR_BF16 && !tensor_supported(p, true)))
     return fail(PSBAX_E_UNSUPPORTED,
-                "tensor engine needs a shared basis (G == 1), S >= 16, L > 0, d <= %d and operands that fit "
+                "tensor engine needs a shared basis (G == 1), L + n > 0, d <= %d and operands that fit "
                 "shared memory (got G=%d d=%d S=%d L=%d n=%d)", TC_MAX_D, p->G, p->d, p->S, p->L, p->n);
   if (p->engine == PSBAX_ENGINE_TENSOR_PROJ && !tensor_proj_supported(p))
     return fail(PSBAX_E_UNSUPPORTED,
-                "tensor projection engine needs a shared basis (G == 1), S >= 16, L > 0, %d <= d <= %d and operands "
+                "tensor projection engine needs a shared basis (G == 1), L + n > 0, %d <= d <= %d and operands "
                 "that fit shared memory (got G=%d d=%d S=%d L=%d n=%d)", TP_MIN_D, TP_MAX_D, p->G, p->d, p->S, p->L, p->n);
   return PSBAX_OK;
 }
@@ -84,7 +84,13 @@ Layout make_layout(const psbax_paths_t* p) {
     l.Lp = l.Lcos + round_up(p->n, 8);
   }
   l.Sp = round_up(p->S, TN);
-  const bool shared = (p->G == 1) && (p->S >= 16) && (l.Lp + l.np_ > 0);
+  // One shared basis: generate every feature once per candidate and contract with all samples (the
+  // sample dimension is padded to 64 anyway).  Only a single path over a low-dimensional set is
+  // better off in the per-sample kernel (measured at N = 1e6, d = 2: S = 1 0.39 ms there against
+  // 0.50 ms here; S = 4 / 8 / 15 took 1.3 / 2.7 / 5.2 ms there, d = 10 with S = 1 22 ms).
+  const bool tensor_asked = p->engine == PSBAX_ENGINE_TENSOR || p->engine == PSBAX_ENGINE_TENSOR_BF16 ||
+                            p->engine == PSBAX_ENGINE_TENSOR_PROJ;
+  const bool shared = (p->G == 1) && (l.Lp + l.np_ > 0) && (p->S >= 2 || p->d >= 5 || tensor_asked);
   if (!shared) l.mode = MODE_PERSAMPLE;
   else if (p->engine == PSBAX_ENGINE_TENSOR) l.mode = MODE_TENSOR;
   else if (p->engine == PSBAX_ENGINE_TENSOR_BF16 || p->engine == PSBAX_ENGINE_TENSOR_PROJ ||

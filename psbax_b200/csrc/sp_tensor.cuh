@@ -387,7 +387,7 @@ __host__ __device__ inline void tc_tile_range(int n, int gx, int c, int* t0, int
 // shape check incl. shared memory with the largest reduction state (top-k, k = KMAX)
 inline bool tensor_supported(const psbax_paths_t* p, bool bf16) {
   const bool lin = p->kernel == PSBAX_KERNEL_LINEAR;
-  if (!(p->G == 1 && p->S >= 16 && (p->L > 0 || p->n > 0) && p->d <= TC_MAX_D)) return false;
+  if (!(p->G == 1 && p->S >= 1 && (p->L > 0 || p->n > 0) && p->d <= TC_MAX_D)) return false;
   Layout l{};
   l.mode = bf16 ? MODE_TENSOR_BF16 : MODE_TENSOR;
   l.dp4 = (p->d <= 2) ? 2 : round_up(p->d, 4);

@@ -544,7 +544,7 @@ def posterior_variance(model, Xq, pending: Optional[torch.Tensor] = None, device
     if engine is None:
         try:
             batch = SamplePathBatch(**params, device=dev, engine="tensor")
-        except _lib.PsbaxError as ex:  # S < 16 pseudo-paths or operands too large for the TF32 images
+        except _lib.PsbaxError as ex:  # operands too large for the TF32 images
             if "engine needs" not in str(ex):
                 raise
             batch = SamplePathBatch(**params, device=dev, engine="auto")

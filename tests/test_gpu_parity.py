@@ -56,7 +56,7 @@ def _tol(p, X=None):
 
 def _tensor_ok(c):
     S, L, d, n, G, kernel, N = c
-    return G == 1 and S >= 16 and (L > 0 or n > 0) and d <= 128
+    return G == 1 and (L > 0 or n > 0) and d <= 128
 
 
 def _proj_ok(c):
@@ -397,7 +397,7 @@ def test_randomised_shapes_all_engines():
         ref = O.eval_paths(p, X.double()).numpy()
         tol = _tol(p)
         engines = ["simt"]
-        if G == 1 and S >= 16 and (L > 0 or n > 0):
+        if G == 1 and (L > 0 or n > 0):
             engines += ["tensor", "tensor_bf16"]
             if 5 <= d <= 32:
                 engines.append("tensor_proj")
