@@ -157,16 +157,17 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const float* sOut,
       const int k = a.k;
       float* tv = e.tv + sl * k;
       int* ti = e.ti + sl * k;
-      // the list's last entry is the admission threshold: kept in registers, re-read after insertions
+      // The list's last entry is the admission threshold: its value stays in a register and is
+      // re-read after insertions.  The pre-filter is y >= threshold; ties on the value are sorted out
+      // by the insertion itself (an entry that is not better than the k-th one is not inserted).
       float thv = tv[k - 1];
-      int thi = ti[k - 1];
-#pragma unroll 1
+      const bool full = (long long)row0 + TM <= N;
+#pragma unroll
       for (int g = 0; g < TM / 32; ++g) {
         const int r = g * 32 + lane;
         const long long row = (long long)row0 + r;
         const float y = fmaf(sOut[sl * OUT_LD + r], a.ystd, a.c0);
-        const bool pass = (row < N) && better(y, (int)row, thv, thi);
-        unsigned int m = __ballot_sync(0xffffffffu, pass);
+        unsigned int m = __ballot_sync(0xffffffffu, (full || row < N) && y >= thv);
         if (m) {
           do {
             const int src = __ffs(m) - 1;
@@ -176,7 +177,6 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const float* sOut,
             topk_insert_warp(tv, ti, k, cv, ci, lane);
           } while (m);
           thv = tv[k - 1];
-          thi = ti[k - 1];
         }
       }
     }

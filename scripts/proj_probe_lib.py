@@ -11,7 +11,7 @@ def make(S, L, d, n, engine, kernel="matern52", seed=0):
     g = torch.Generator().manual_seed(seed)
     omega = (torch.randn(1, L, d, generator=g) * 3.0).to(dev)
     bias = (torch.rand(1, L, generator=g) * 6.2831853).to(dev)
-    W = (torch.randn(S, L, generator=g) * (2.0 / L) ** 0.5).to(dev)
+    W = (torch.randn(S, L, generator=g) * (2.0 / max(L, 1)) ** 0.5).to(dev)
     kw = {}
     if n:
         kw = dict(Xtrain=torch.rand(n, d, generator=g).to(dev), inv_ls=torch.full((d,), 2.0).to(dev),
