@@ -375,10 +375,31 @@ def eval_path_grad(p: PathParams, X: torch.Tensor, s: int) -> torch.Tensor:
 
 
 def path_scale(p: PathParams, X: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Per-sample magnitude the 1e-4 tolerance is relative to:
-    y_std * max(1, ||W_s||_2 + m * ||V_s||_2) — the natural forward-error scale of
-    the two dot products.  |cos| <= 1 and |kappa| <= 1 give m = 1; the linear kernel's
-    features x . x' are unbounded, there m = max |feature| over the candidates X."""
+    """Per-sample magnitude THE 1e-4 PARITY TOLERANCE is relative to (SURVEY.md section 8c:
+    "y_std * sqrt(outputscale) * ||w_s|| / sqrt(L)-like path scale"): the magnitude of the path,
+
+        y_std * max(1, ||W_s||_2)              (W already carries sqrt(2 * outputscale / L)).
+
+    There is deliberately NO ||V_s|| term: the Matheron update weights V = (K + sigma^2 I)^-1 (...)
+    are large and cancel in k(x, X) . V_s (||V_s|| ~ 80 on the bench problem against a path of
+    magnitude ~1), so a scale that contains them is far looser than "1e-4 relative" — see
+    ``forward_error_scale`` for that diagnostic.  Linear-kernel rows (the DKGP weight-space form,
+    ``src/utils.py:153-206``) are different: there V *is* the weight vector w_s on features
+    x . x' that are not bounded by 1, so its norm times the largest |feature| over the candidates
+    X is the path magnitude."""
+    s = p.W.norm(dim=1) if p.L > 0 else torch.zeros(p.S, dtype=DTYPE)
+    if p.n > 0 and p.kernel == "linear":
+        m = 1.0
+        if X is not None:
+            m = max(1.0, float(((X.to(DTYPE) * p.inv_ls) @ p.Xtrain.T).abs().max()))
+        s = s + m * p.V.norm(dim=1)
+    return abs(p.y_std) * torch.clamp(s, min=1.0)
+
+
+def forward_error_scale(p: PathParams, X: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """DIAGNOSTIC ONLY (not the parity criterion): y_std * max(1, ||W_s||_2 + m ||V_s||_2), the
+    forward-error scale of the two dot products.  Round 1 used this as the tolerance scale; on
+    Matheron draws it is 20-90x looser than the path magnitude."""
     s = p.W.norm(dim=1) if p.L > 0 else torch.zeros(p.S, dtype=DTYPE)
     if p.n > 0:
         m = 1.0

@@ -9,11 +9,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpsbax_b200.so")
-SOURCES = ["psbax_b200.cu"]
+SOURCES = ["psbax_b200.cu", "simt.cu", "tensor_bf16.cu", "tensor_tf32.cu", "tensor_proj.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-lcuda",
+    "-Xcompiler", "-fPIC",
 ]
+LINK_FLAGS = ["-shared", "-lcuda"]
 
 
 def _nvcc() -> str:
@@ -38,13 +39,32 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
     out = OUT.replace(".so", "_trace.so") if trace else OUT
     if not force and not trace and not _stale():
         return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-DPSBAX_TC_TRACE=1"] if trace else []) + \
-        (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+    # one object per translation unit, compiled in parallel, then one link
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = os.path.join(HERE, "build", "trace" if trace else "obj")
+    os.makedirs(objdir, exist_ok=True)
+    flags = NVCC_FLAGS + (["-DPSBAX_TC_TRACE=1"] if trace else []) + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        res = subprocess.run([_nvcc()] + flags + ["-c", "-o", obj, src], cwd=CSRC, capture_output=True, text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    bad = False
+    for src, _obj, res in results:
+        if verbose or res.returncode != 0:
+            sys.stderr.write(f"==== {src}\n" + res.stdout + res.stderr)
+        bad = bad or res.returncode != 0
+    if bad:
         raise RuntimeError("nvcc failed building libpsbax_b200.so")
+    res = subprocess.run([_nvcc()] + NVCC_FLAGS + LINK_FLAGS + ["-o", out] + [o for _s, o, _r in results],
+                         cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libpsbax_b200.so")
     return out
 
 

@@ -4,11 +4,18 @@
 #include <cstdio>
 #include <cstring>
 
+#define PSBAX_TU_API 1
 #include "sp_common.cuh"
 #include "sp_extra.cuh"
+#include "sp_host_kernels.cuh"
 #include "sp_simt.cuh"
 #include "sp_tensor.cuh"
 #include "sp_tensor_proj.cuh"
+
+namespace psbax {
+// simt.cu: the FFMA / MUFU kernels
+int simt_launch(int epi, const KArgs& a, dim3 grid, cudaStream_t st, char* err, size_t errlen);
+}
 
 using namespace psbax;
 
@@ -102,7 +109,8 @@ Layout make_layout(const psbax_paths_t* p) {
   if (is_tensor_mode(l.mode)) {
     const bool want_proj = p->engine == PSBAX_ENGINE_TENSOR_PROJ ||
                            (p->engine == PSBAX_ENGINE_AUTO && p->d >= TP_AUTO_MIN_D);
-    l.Kp = round_up(l.Lp_ft + l.np_, TP_TKB);  // what the projection variant would use (tp_supported reads it)
+    l.tkb = TP_TKB;
+    layout_blocks(l);  // what the projection variant would use (tp_supported reads Kp)
     if (want_proj && tp_supported(l)) {  // [W;V] images as for the generic kernel (32-feature bf16 blocks)
       l.tc_proj = 1;
       l.tc_generic = 1;
@@ -111,7 +119,7 @@ Layout make_layout(const psbax_paths_t* p) {
     }
     l.tkb = tc_tkb(l.mode == MODE_TENSOR_BF16, l.tc_generic != 0);
   }
-  l.Kp = round_up(l.Lp_ft + l.np_, l.tkb);
+  layout_blocks(l);
   size_t off = 0;
   l.off_invls = off; off += round_up(l.dp4, 4);
   l.off_ft = off;    off += (size_t)l.Kp * l.OS;
@@ -137,51 +145,6 @@ void grid_for(const Layout& l, long long N, int sms, int* gx, int* gy, int* ntil
   g = (nt + tpc - 1) / (tpc > 0 ? tpc : 1);
   if (g < 1) g = 1;
   *gx = (int)g;
-}
-
-size_t simt_smem_bytes(const Layout& l, int epi, int k, bool shared, bool generic) {
-  size_t state = round_up((int)epi_smem_floats(epi, k), 4);
-  size_t tile = (size_t)TN * OUT_LD;
-  if (shared) {
-    size_t work = (size_t)TK * TM + (size_t)TK * TN + (size_t)TK * l.OS + round_up(l.dp4, 4) +
-                  (generic ? (size_t)l.dp4 * TM : 0);
-    if (work > tile) tile = work;
-  } else {
-    tile += round_up(l.dp4, 4) + (generic ? (size_t)l.dp4 * TM : 0);
-  }
-  return (state + tile) * sizeof(float);
-}
-
-template <typename K>
-int launch_simt(K kern, const KArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-  if (smem > 227 * 1024) return fail(PSBAX_E_UNSUPPORTED, "shared memory %zu B exceeds 227 KB (d too large)", smem);
-  if (smem > 48 * 1024)
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, NTHREADS, smem, st>>>(a);
-  CUDA_TRY(cudaGetLastError());
-  return PSBAX_OK;
-}
-
-template <int EPI>
-int dispatch_simt(const KArgs& a, dim3 grid, cudaStream_t st) {
-  const Layout& l = a.lay;
-  const bool shared = l.mode != MODE_PERSAMPLE;
-  if (shared) {
-    switch (l.dp4) {
-      case 2:  return launch_simt(k_shared_simt<2, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, false), st);
-      case 4:  return launch_simt(k_shared_simt<4, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, false), st);
-      case 8:  return launch_simt(k_shared_simt<8, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, false), st);
-      case 12: return launch_simt(k_shared_simt<12, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, false), st);
-      case 16: return launch_simt(k_shared_simt<16, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, false), st);
-      default: return launch_simt(k_shared_simt<0, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, true, true), st);
-    }
-  }
-  switch (l.dp4) {
-    case 2:  return launch_simt(k_persample<2, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, false, false), st);
-    case 4:  return launch_simt(k_persample<4, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, false, false), st);
-    case 8:  return launch_simt(k_persample<8, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, false, false), st);
-    default: return launch_simt(k_persample<0, EPI>, a, grid, simt_smem_bytes(l, EPI, a.k, false, true), st);
-  }
 }
 
 struct Prepared {
@@ -297,7 +260,7 @@ int psbax_eval_values(const psbax_paths_t* paths, const void* pack, const float*
   pr.a.ld_out = ld_out;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_tensor_mode(pr.a.lay.mode)) return tensor_launch_any(EPI_VALUES, pr.a, pr.sms, st, g_err, sizeof(g_err));
-  return dispatch_simt<EPI_VALUES>(pr.a, pr.grid, st);
+  return simt_launch(EPI_VALUES, pr.a, pr.grid, st, g_err, sizeof(g_err));
 }
 
 int psbax_sumsq_scratch_bytes(const psbax_paths_t* paths, int64_t N, size_t* bytes) {
@@ -325,7 +288,7 @@ int psbax_eval_sumsq(const psbax_paths_t* paths, const void* pack, const float* 
   pr.a.rowsq = chunks > 1 ? static_cast<float*>(scratch) : out;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_tensor_mode(pr.a.lay.mode)) rc = tensor_launch_any(EPI_VALUES, pr.a, pr.sms, st, g_err, sizeof(g_err));
-  else rc = dispatch_simt<EPI_VALUES>(pr.a, pr.grid, st);
+  else rc = simt_launch(EPI_VALUES, pr.a, pr.grid, st, g_err, sizeof(g_err));
   if (rc) return rc;
   if (chunks > 1) {
     k_sumsq_finalize<<<(unsigned)((N + 255) / 256 > 2368 ? 2368 : (N + 255) / 256), 256, 0, st>>>(
@@ -362,7 +325,7 @@ int psbax_eval_levelset(const psbax_paths_t* paths, const void* pack, const floa
   a.p_arg = reinterpret_cast<int*>(a.p_max + per);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_tensor_mode(l.mode)) rc = tensor_launch_any(EPI_LEVELSET, a, pr.sms, st, g_err, sizeof(g_err));
-  else rc = dispatch_simt<EPI_LEVELSET>(a, pr.grid, st);
+  else rc = simt_launch(EPI_LEVELSET, a, pr.grid, st, g_err, sizeof(g_err));
   if (rc) return rc;
   k_levelset_finalize<<<(l.S + 127) / 128, 128, 0, st>>>(a.p_cnt, a.p_max, a.p_arg, parts, l.Sp, l.S,
                                                        row_offset, reinterpret_cast<long long*>(count),
@@ -395,7 +358,7 @@ int psbax_eval_topk(const psbax_paths_t* paths, const void* pack, const float* X
   a.p_ti = reinterpret_cast<int*>(a.p_tv + per);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (is_tensor_mode(l.mode)) rc = tensor_launch_any(EPI_TOPK, a, pr.sms, st, g_err, sizeof(g_err));
-  else rc = dispatch_simt<EPI_TOPK>(a, pr.grid, st);
+  else rc = simt_launch(EPI_TOPK, a, pr.grid, st, g_err, sizeof(g_err));
   if (rc) return rc;
   k_topk_merge<int><<<l.S, 128, 0, st>>>(a.p_tv, a.p_ti, parts, l.Sp, k, row_offset, out_val,
                                         reinterpret_cast<long long*>(out_idx));

@@ -40,7 +40,11 @@ struct Layout {
   int Lp_ft;  // RFF rows present in ft / wv (Lp in shared modes, 0 in per-sample mode)
   int Lcos;   // feature rows below Lcos use cos(arg); rows in [Lcos, Lp) are linear-kernel rows: arg itself
   int lin_n;  // number of linear-kernel rows (PSBAX_KERNEL_LINEAR), else 0
-  int Kp;     // rows of ft / wv, multiple of TK
+  int Kp;     // rows of ft / wv
+  int kk0;    // first exact-kernel row of ft / wv (== Lp_ft unless the BF16x3 engine pads the RFF section
+              // to whole blocks); rows in [Lp_ft, kk0) are padding (zero table rows, zero weights)
+  int nkb_r;  // tensor engines: feature blocks of tkb rows covering [0, kk0) (every block when nkb_k == 0)
+  int nkb_k;  // BF16x3 engine: exact-kernel blocks of tkb / 2 rows each, contracted in 3xTF32 (see below)
   int Sp;     // S rounded up to TN
   int mode;
   int tkb;         // tensor engines: features per block (32, or 64 for BF16x3 with x in registers)
@@ -48,6 +52,29 @@ struct Layout {
   int tc_proj;     // BF16x3 engine, projection variant: feature arguments computed by 3xTF32 MMAs (sp_tensor_proj.cuh)
   size_t off_invls, off_ft, off_wv, off_pb, off_tc, total_floats;
 };
+
+// Block structure of the feature axis.  The BF16x3 tensor engine keeps the exact-kernel rows
+// k(x, X_train) . V_s out of the bf16 split: V = (K + sigma^2 I)^-1 (...) has large entries that
+// cancel in the sum, and a 2^-17 operand error there is far above 1e-4 of the path magnitude.  Its
+// feature axis is therefore [RFF rows, padded to whole blocks of tkb][kernel rows, blocks of tkb / 2]
+// and the kernel blocks are contracted with the 3xTF32 split (same stage footprints: tkb bf16
+// features and tkb / 2 tf32 features fill the same tensor-memory columns and operand bytes).
+__host__ __device__ inline void layout_blocks(Layout& l) {
+  const bool mixed = (l.mode == MODE_TENSOR_BF16) && l.np_ > 0;
+  if (mixed) {
+    const int kf = l.tkb / 2;
+    const int npk = round_up(l.np_, kf);
+    l.kk0 = round_up(l.Lp_ft, l.tkb);
+    l.Kp = l.kk0 + npk;
+    l.nkb_r = l.kk0 / l.tkb;
+    l.nkb_k = npk / kf;
+  } else {
+    l.kk0 = l.Lp_ft;
+    l.Kp = round_up(l.Lp_ft + l.np_, l.tkb);
+    l.nkb_r = l.Kp / l.tkb;
+    l.nkb_k = 0;
+  }
+}
 
 struct KArgs {
   Layout lay;
@@ -107,28 +134,32 @@ __device__ __forceinline__ float kernel_profile(float r2, int kernel) {
   return fast_ex2(-LOG2E * r);
 }
 
-// eight profiles at once: one (warp-uniform) switch, straight-line bodies
-__device__ __forceinline__ void kernel_profile8(const float (&r2)[8], float (&v)[8], int kernel) {
+// NP profiles at once: one (warp-uniform) switch, straight-line bodies
+template <int NP>
+__device__ __forceinline__ void kernel_profile_n(const float (&r2)[NP], float (&v)[NP], int kernel) {
   constexpr float LOG2E = 1.4426950408889634f;
   if (kernel == PSBAX_KERNEL_MATERN52) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NP; ++j) {
       const float s = 2.2360679774997896f * fast_sqrt(r2[j]);
       v[j] = (1.0f + s + 1.6666666666666667f * r2[j]) * fast_ex2(-LOG2E * s);
     }
   } else if (kernel == PSBAX_KERNEL_RBF) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fast_ex2(-0.5f * LOG2E * r2[j]);
+    for (int j = 0; j < NP; ++j) v[j] = fast_ex2(-0.5f * LOG2E * r2[j]);
   } else if (kernel == PSBAX_KERNEL_MATERN32) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NP; ++j) {
       const float s = 1.7320508075688772f * fast_sqrt(r2[j]);
       v[j] = (1.0f + s) * fast_ex2(-LOG2E * s);
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = fast_ex2(-LOG2E * fast_sqrt(r2[j]));
+    for (int j = 0; j < NP; ++j) v[j] = fast_ex2(-LOG2E * fast_sqrt(r2[j]));
   }
+}
+__device__ __forceinline__ void kernel_profile8(const float (&r2)[8], float (&v)[8], int kernel) {
+  kernel_profile_n<8>(r2, v, kernel);
 }
 
 // d kappa / d(r2) * 2  (so that grad_x = dk2 * diff * inv_ls), used by the gradient kernel

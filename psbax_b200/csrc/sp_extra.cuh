@@ -255,8 +255,8 @@ __global__ void __launch_bounds__(128) k_eval_grad(const __grid_constant__ KArgs
       coef[l] = -w * sn;
     }
   }
-  const float* __restrict__ FTK = a.pack + lay.off_ft + (size_t)lay.Lp_ft * lay.OS;
-  const float* __restrict__ VT = a.pack + lay.off_wv + (size_t)lay.Lp_ft * lay.Sp;
+  const float* __restrict__ FTK = a.pack + lay.off_ft + (size_t)lay.kk0 * lay.OS;
+  const float* __restrict__ VT = a.pack + lay.off_wv + (size_t)lay.kk0 * lay.Sp;
   for (int j = tid; j < lay.n; j += blockDim.x) {
     const float* r = FTK + (size_t)j * lay.OS;
     float r2 = 0.f;

@@ -33,6 +33,7 @@
 //                      ACT = 64 (TF32, 2 stages) or 32 (BF16 pairs, 4 stages)
 #pragma once
 #include "sp_common.cuh"
+#include <cstdio>
 #include <type_traits>
 
 #include "sp_simt.cuh"
@@ -95,7 +96,7 @@ inline bool is_tensor_mode(int mode) { return mode == MODE_TENSOR || mode == MOD
 // [chunks][nkb] images of BBYTES
 inline size_t tensor_pack_floats(const Layout& l) {
   const bool bf = l.mode == MODE_TENSOR_BF16;
-  return (size_t)(l.Sp / TN) * (l.Kp / l.tkb) * (tc_bbytes(bf, l.tc_generic != 0) / 4);
+  return (size_t)(l.Sp / TN) * (l.nkb_r + l.nkb_k) * (tc_bbytes(bf, l.tc_generic != 0) / 4);
 }
 
 // ---------------------------------------------------------------------------------
@@ -352,7 +353,11 @@ __host__ __device__ inline TcSmem tc_smem_layout_impl(const Layout& l, int epi, 
   const uint32_t tkb = tc_tkb(bf, generic), bbytes = tc_bbytes(bf, generic);
   s.nsb = generic ? 4u : (bbytes == 16384u ? 4u : 8u);
   s.stage = bbytes + (generic ? tkb * l.OS * 4 : 0u);
-  const uint32_t kp = (uint32_t)round_up(l.Lp + l.np_, (int)tkb);
+  Layout lb = l;  // rows of the (resident) feature table for this block size
+  lb.Lp_ft = l.Lp;
+  lb.tkb = (int)tkb;
+  layout_blocks(lb);
+  const uint32_t kp = (uint32_t)lb.Kp;
   uint32_t o = 0;
   s.b = o;     o += s.nsb * s.stage;
   s.ft = o;    o += generic ? 0u : kp * l.OS * 4;                         // resident table (small d)
@@ -420,33 +425,49 @@ inline int tensor_parts(const Layout& l, long long N, int sms) {
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint16_t bf16_rn_bits(float x) { return (uint16_t)(cvt_bf16x2(x, x) & 0xffffu); }
 
+#ifdef PSBAX_TU_API  // the pack kernel lives in the API translation unit only
 __global__ void k_tensor_pack(Layout lay, float* __restrict__ pack) {
   const float* __restrict__ wv = pack + lay.off_wv;
   const bool bf = lay.mode == MODE_TENSOR_BF16;
   const int tkb = lay.tkb;
-  const int nkb = lay.Kp / tkb;
-  const int img_elems = 128 * tkb;                 // elements per image
-  const int kcore = bf ? 8 : 4;                    // elements per 16-byte core-matrix row
-  const int group_elems = 8 * tkb;                 // elements per 8-row group (SBO)
-  const size_t total = (size_t)(lay.Sp / TN) * nkb * img_elems;
-  float* __restrict__ tc32 = pack + lay.off_tc;
-  uint16_t* __restrict__ tc16 = reinterpret_cast<uint16_t*>(pack + lay.off_tc);
+  const int nkb = lay.nkb_r + lay.nkb_k;
+  const int wpi = bf ? 64 * tkb : 128 * tkb;  // 4-byte words per image (BBYTES / 4)
+  const size_t total = (size_t)(lay.Sp / TN) * nkb * wpi;
+  uint32_t* __restrict__ tc = reinterpret_cast<uint32_t*>(pack + lay.off_tc);
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
-    const int within = (int)(idx % img_elems);
-    const size_t img = idx / img_elems;
+    const int within = (int)(idx % wpi);
+    const size_t img = idx / wpi;
     const int kb = (int)(img % nkb), cy = (int)(img / nkb);
-    const int rg = within / group_elems, rem = within % group_elems;
-    const int kc = rem / (8 * kcore), r8 = (rem / kcore) & 7, ke = rem % kcore;
-    const int r = rg * 8 + r8, k = kc * kcore + ke;
-    const float x = wv[(size_t)(kb * tkb + k) * lay.Sp + cy * TN + (r & 63)];
-    if (bf) {
-      const uint16_t b1 = bf16_rn_bits(x);
-      const float x1 = __uint_as_float((uint32_t)b1 << 16);
-      tc16[idx] = (r < 64) ? b1 : bf16_rn_bits(x - x1);
+    if (bf && kb < lay.nkb_r) {
+      // bf16 image of tkb features: word = elements (2 within, 2 within + 1), adjacent in k
+      const int group_elems = 8 * tkb;
+      uint32_t word = 0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int el = 2 * within + e;
+        const int rg = el / group_elems, rem = el % group_elems;
+        const int kc = rem / 64, r8 = (rem >> 3) & 7, ke = rem & 7;
+        const int r = rg * 8 + r8, k = kc * 8 + ke;
+        const float x = wv[(size_t)(kb * tkb + k) * lay.Sp + cy * TN + (r & 63)];
+        const uint16_t b1 = bf16_rn_bits(x);
+        const float x1 = __uint_as_float((uint32_t)b1 << 16);
+        const uint16_t bits = (r < 64) ? b1 : bf16_rn_bits(x - x1);
+        word |= (uint32_t)bits << (16 * e);
+      }
+      tc[idx] = word;
     } else {
+      // tf32 image: kf features (the whole block in the 3xTF32 engine, an exact-kernel block of
+      // tkb / 2 rows in the BF16x3 engine)
+      const int kf = bf ? tkb / 2 : tkb;
+      const int k0 = bf ? lay.kk0 + (kb - lay.nkb_r) * kf : kb * tkb;
+      const int group_elems = 8 * kf;
+      const int rg = within / group_elems, rem = within % group_elems;
+      const int kc = rem / 32, r8 = (rem >> 2) & 7, ke = rem & 3;
+      const int r = rg * 8 + r8, k = kc * 4 + ke;
+      const float x = wv[(size_t)(k0 + k) * lay.Sp + cy * TN + (r & 63)];
       const float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);  // round to TF32
-      tc32[idx] = (r < 64) ? hi : (x - hi);
+      tc[idx] = __float_as_uint((r < 64) ? hi : (x - hi));
     }
   }
 }
@@ -455,6 +476,8 @@ inline int tensor_pack(const Layout& l, float* pack, cudaStream_t st) {
   k_tensor_pack<<<296, 256, 0, st>>>(l, pack);
   return cudaGetLastError() == cudaSuccess ? PSBAX_OK : PSBAX_E_CUDA;
 }
+
+#endif  // PSBAX_TU_API
 
 // ---------------------------------------------------------------------------------
 // Level-set epilogue with register-resident state.  The epilogue warps are on the critical
@@ -561,7 +584,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
 
   constexpr int TKB = C::TKB;
   constexpr int TC_FPW = TKB / (TC_NPROD / 4);  // features per producer warp per block
-  const int nkb = lay.Kp / TKB;
+  // feature blocks: nkb_r blocks of TKB rows (RFF / linear rows; every block in the 3xTF32 engine),
+  // then (BF16x3 engine) nkb_k exact-kernel blocks of TKB / 2 rows contracted in 3xTF32
+  const int nkb_r = lay.nkb_r;
+  const int nkb = lay.nkb_r + lay.nkb_k;
+  constexpr int KF = TKB / 2;               // rows of an exact-kernel block
   constexpr bool GEN = (DP == 0);           // generic d: x in shared memory, table blocks streamed
   constexpr int OSC = (DP + 1 + 3) / 4 * 4; // row stride of the table for this DP (compile time)
   const int OS = GEN ? lay.OS : OSC;
@@ -613,10 +640,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         const uint32_t bs = it % NSB, ph = (it / NSB) & 1;
         mbar_wait_hybrid(&b_empty[bs], ph ^ 1, lane);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&b_full[bs], C::BBYTES + (GEN ? ftbytes : 0u));
+          // table rows of the block (generic d): TKB rows from kb * TKB, or the KF rows of an exact-kernel block
+          const bool kblk = BF && kb >= nkb_r;
+          const uint32_t fb = kblk ? ftbytes / 2 : ftbytes;
+          const size_t frow = kblk ? (size_t)lay.kk0 + (size_t)(kb - nkb_r) * KF : (size_t)kb * TKB;
+          mbar_arrive_expect_tx(&b_full[bs], C::BBYTES + (GEN ? fb : 0u));
           bulk_g2s(sB + bs * STAGE, gB + (size_t)kb * C::BBYTES, C::BBYTES, &b_full[bs]);
           if constexpr (GEN)
-            bulk_g2s(sB + bs * STAGE + C::BBYTES, gFT + (size_t)kb * ftbytes, ftbytes, &b_full[bs]);
+            bulk_g2s(sB + bs * STAGE + C::BBYTES, gFT + frow * OS * 4, fb, &b_full[bs]);
         }
         __syncwarp();
       }
@@ -657,7 +688,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
                             mbar_test(&b_full[nit % NSB], (nit / NSB) & 1);
             ready = __all_sync(0xffffffffu, ok) != 0;
           }
-          if (elect_one()) {
+          if (BF && kb >= nkb_r) {
+            // exact-kernel block: KF features as TF32 hi | lo (A columns [0, KF) | [KF, 2 KF)), K = 8 per MMA
+            if (elect_one()) {
+              constexpr uint32_t IDESC_K = umma_idesc_tf32(TN);
+              constexpr uint32_t SBO_K = KF * 4 * 8, SPLIT2_K = 8 * SBO_K;
+#pragma unroll
+              for (int ks = 0; ks < KF / 8; ++ks) {
+                const uint64_t b1 = umma_desc_kmajor(bbase + ks * 256, 128, SBO_K);
+                const uint64_t b2 = umma_desc_kmajor(bbase + SPLIT2_K + ks * 256, 128, SBO_K);
+                const uint32_t a1 = a_base + t * C::ACT + ks * 8, a2 = a1 + C::ACT / 2;
+                const uint32_t d = d_addr + t * TN;
+                tc_mma_ts(d, a1, b1, IDESC_K, (kb | ks) ? 1u : 0u);
+                tc_mma_ts(d, a1, b2, IDESC_K, 1u);
+                tc_mma_ts(d, a2, b1, IDESC_K, 1u);
+              }
+              if (t == TC_TILES - 1) {
+                tc_commit(&b_empty[bs]);
+                tc_commit(&a_empty[as]);
+                if (kb == nkb - 1) tc_commit(&d_full[buf]);
+              }
+            }
+          } else if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < C::KSTEPS; ++ks) {
               const uint64_t b1 = umma_desc_kmajor(bbase + ks * C::B_KSTEP, 128, C::B_SBO);
@@ -731,6 +783,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         constexpr bool EARLY = GEN || DP >= 12;
         uint32_t s1[NG][TC_TILES][C::WCOLS], s2[NG][TC_TILES][C::WCOLS];
         const uint32_t bs = it % NSB;
+        const bool kblk = BF && kb >= nkb_r;
+        if (kblk) {
+          // ---- exact-kernel block of the BF16x3 engine: KF features, TF32 hi | lo operands ----
+          // x in registers: KF = 32, 8 features per warp; generic d: KF = 16, 4 features per warp.
+          const int kbk = kb - nkb_r;
+          constexpr int KW = GEN ? 4 : 8;  // features per warp = tensor-memory columns per operand half
+          uint32_t khi[TC_TILES][KW], klo[TC_TILES][KW];
+          {
+            float r2[TC_TILES][KW];
+            if constexpr (GEN) {
+              mbar_wait_hybrid(&b_full[bs], (it / NSB) & 1, lane);  // the block's table rows sit behind the B image
+              const float* ft = reinterpret_cast<const float*>(sB + bs * STAGE + C::BBYTES) + h * KW * OS;
+              uint64_t acc2[KW];
+#pragma unroll
+              for (int j = 0; j < KW; ++j) acc2[j] = 0ull;
+              const uint64_t* xr = reinterpret_cast<const uint64_t*>(sX) + q * 32 + lane;
+              for (int i0 = 0; i0 < lay.dp4; i0 += 4) {
+                uint64_t xa[4];
+                float il4[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { xa[c] = xr[(i0 + c) * TM]; il4[c] = sIl[i0 + c]; }
+#pragma unroll
+                for (int j = 0; j < KW; ++j) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
+                  const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    const uint64_t df = ffma2(xa[c], pack2(il4[c], il4[c]), pack2(wv4[c], wv4[c]));
+                    acc2[j] = ffma2(df, df, acc2[j]);
+                  }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < KW; ++j) unpack2(acc2[j], r2[0][j], r2[1][j]);
+              __syncwarp();
+            } else {
+              const float* ft = sFT + (lay.kk0 + kbk * KF + h * KW) * OSC;
+#pragma unroll
+              for (int j = 0; j < KW; ++j) {
+                float w[OSC];
+                load_row<OSC>(ft + j * OSC, w);
+                uint64_t acc = pack2(0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < DP; ++i) {
+                  const uint64_t df = ffma2(xp[i], pack2(sIl[i], sIl[i]), pack2(w[i], w[i]));
+                  acc = ffma2(df, df, acc);
+                }
+                unpack2(acc, r2[0][j], r2[1][j]);
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < TC_TILES; ++t) {
+              float kv[KW];
+              kernel_profile_n<KW>(r2[t], kv, lay.kernel);
+#pragma unroll
+              for (int j = 0; j < KW; ++j) {
+                const uint32_t hb = __float_as_uint(kv[j]) & 0xffffe000u;
+                khi[t][j] = hb;
+                klo[t][j] = __float_as_uint(kv[j] - __uint_as_float(hb));
+              }
+            }
+          }
+          mbar_wait_hybrid_sleep<PSBAX_AEMPTY_HINT>(&a_empty[as], aph ^ 1, lane);
+          tc_fence_after();
+#pragma unroll
+          for (int t = 0; t < TC_TILES; ++t) {
+            const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + h * KW;
+            if constexpr (GEN) {
+              tc_st4(lane_addr + col, khi[t]);
+              tc_st4(lane_addr + col + C::ACT / 2, klo[t]);
+            } else {
+              tc_st8(lane_addr + col, khi[t]);
+              tc_st8(lane_addr + col + C::ACT / 2, klo[t]);
+            }
+          }
+        } else {
         if constexpr (GEN) {  // the table block of this K-block arrives with the B image
           mbar_wait_hybrid(&b_full[bs], (it / NSB) & 1, lane);
         }
@@ -746,7 +874,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           const float* ft = ftb + g * 8 * OS;
           const bool lin = PURE ? false : kbase >= lay.Lcos;  // linear-kernel rows: identity activation (warp-uniform)
           float v[TC_TILES][8];
-          if constexpr (GEN) {
+          // BF16x3 engine: the rows between the RFF section and the first exact-kernel block are
+          // padding (zero weights): nothing to evaluate
+          const bool pad = BF && !PURE && kbase >= lay.Lp_ft;
+          if (pad) {
+#pragma unroll
+            for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[t][j] = 0.f;
+          } else if constexpr (GEN) {
             // x pairs from shared memory, 4 dimensions at a time, reused by the 8 features; packed FP32
             // over the thread's two rows with the table entry (and inv_ls) as scalar-broadcast operands
             const bool rff = kbase < lay.Lp_ft;
@@ -918,6 +1054,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
 #pragma unroll
           for (int g = 0; g < NG; ++g) group(std::false_type{}, g);
         }
+        }  // !kblk
         if constexpr (GEN) {  // done reading the streamed table block
           __syncwarp();
           if (lane == 0) mbar_arrive(&b_empty[bs]);
@@ -1019,15 +1156,18 @@ int tensor_launch_epi(const KArgs& a0, int sms, cudaStream_t st, char* err, size
   return PSBAX_OK;
 }
 
+// one translation unit per operand format instantiates the kernels (tensor_bf16.cu / tensor_tf32.cu)
+int tensor_launch_bf16(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen);
+int tensor_launch_tf32(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen);
+template <bool BF>
+int tensor_launch_fmt(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
+  if (epi == EPI_VALUES) return tensor_launch_epi<EPI_VALUES, BF>(a, sms, st, err, errlen);
+  if (epi == EPI_LEVELSET) return tensor_launch_epi<EPI_LEVELSET, BF>(a, sms, st, err, errlen);
+  return tensor_launch_epi<EPI_TOPK, BF>(a, sms, st, err, errlen);
+}
 inline int tensor_launch(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
-  if (a.lay.mode == MODE_TENSOR_BF16) {
-    if (epi == EPI_VALUES) return tensor_launch_epi<EPI_VALUES, true>(a, sms, st, err, errlen);
-    if (epi == EPI_LEVELSET) return tensor_launch_epi<EPI_LEVELSET, true>(a, sms, st, err, errlen);
-    return tensor_launch_epi<EPI_TOPK, true>(a, sms, st, err, errlen);
-  }
-  if (epi == EPI_VALUES) return tensor_launch_epi<EPI_VALUES, false>(a, sms, st, err, errlen);
-  if (epi == EPI_LEVELSET) return tensor_launch_epi<EPI_LEVELSET, false>(a, sms, st, err, errlen);
-  return tensor_launch_epi<EPI_TOPK, false>(a, sms, st, err, errlen);
+  return a.lay.mode == MODE_TENSOR_BF16 ? tensor_launch_bf16(epi, a, sms, st, err, errlen)
+                                        : tensor_launch_tf32(epi, a, sms, st, err, errlen);
 }
 
 }  // namespace psbax

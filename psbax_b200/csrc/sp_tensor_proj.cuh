@@ -46,7 +46,7 @@ struct TpSmem {
 __host__ __device__ inline TpSmem tp_smem_layout(const Layout& l, int epi, int k) {
   TpSmem s{};
   s.ftk = TP_WBYTES + tp_obytes(l.d);  // offset of the table block inside a stage
-  s.stage = s.ftk + (l.np_ > 0 ? (uint32_t)TP_TKB * l.OS * 4 : 0u);
+  s.stage = s.ftk + (l.np_ > 0 ? (uint32_t)(TP_TKB / 2) * l.OS * 4 : 0u);  // + the 16 table rows of an exact-kernel block
   // everything but the ring first; the ring takes what is left (a stage is released only after
   // its contraction completes and a bulk copy takes ~2000 cycles, so depth 4 starved the issuers)
   const uint32_t fixed = (l.n > 0 ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u) + TC_TILES * TN * OUT_LD * 4 +
@@ -82,19 +82,23 @@ inline bool tensor_proj_supported(const psbax_paths_t* p) {
   l.n = lin ? 0 : p->n;
   l.dp4 = (p->d <= 2) ? 2 : round_up(p->d, 4);
   l.OS = round_up(l.dp4 + 1, 4);
+  l.Lp = round_up(p->L, 8) + (lin ? round_up(p->n, 8) : 0);
+  l.Lp_ft = l.Lp;
   l.np_ = lin ? 0 : round_up(p->n, 8);
-  l.Kp = round_up(round_up(p->L, 8) + round_up(p->n, 8), TP_TKB);
+  l.tkb = TP_TKB;
+  layout_blocks(l);
   return tp_supported(l);
 }
 // floats appended to the tensor pack: one (hi | lo) Omega_aug image per 32-feature block
-__host__ __device__ inline size_t tp_pack_floats(const Layout& l) { return (size_t)(l.Kp / TP_TKB) * (tp_obytes(l.d) / 4); }
+__host__ __device__ inline size_t tp_pack_floats(const Layout& l) { return (size_t)(l.nkb_r + l.nkb_k) * (tp_obytes(l.d) / 4); }
 
+#ifdef PSBAX_TU_API  // the pack kernel lives in the API translation unit only
 // Omega_aug images: UMMA canonical no-swizzle K-major, N = 32 feature rows, K = Kx.
 //   float offset inside a split image: (r/8)*(Kx/4)*32 + (k/4)*32 + (r%8)*4 + (k%4)
 __global__ void k_tensor_proj_pack(Layout lay, float* __restrict__ pack, size_t off_om) {
   const float* __restrict__ ft = pack + lay.off_ft;
   float* __restrict__ om = pack + off_om;
-  const int kx = tp_kx(lay.d), nkb = lay.Kp / TP_TKB;
+  const int kx = tp_kx(lay.d), nkb = lay.nkb_r + lay.nkb_k;  // (images of exact-kernel blocks stay zero: no projection)
   const int img = 32 * kx;  // floats per split image
   const size_t total = (size_t)nkb * 2 * img;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -107,7 +111,7 @@ __global__ void k_tensor_proj_pack(Layout lay, float* __restrict__ pack, size_t 
     const int r = rg * 8 + r8, k = kc * 4 + ke;
     const int row = kb * TP_TKB + r;  // feature row of the table
     float x = 0.f;
-    if (row < lay.Lp_ft) {  // cos / linear rows: (omega | bias at dp4); kernel rows project to 0
+    if (kb < lay.nkb_r && row < lay.Lp_ft) {  // cos / linear rows: (omega | bias at dp4); other rows project to 0
       if (k < lay.d) x = ft[(size_t)row * lay.OS + k];
       else if (k == lay.d && tp_bias_in_x(lay.d)) x = ft[(size_t)row * lay.OS + lay.dp4];
     }
@@ -121,6 +125,8 @@ inline int tensor_proj_pack(const Layout& l, float* pack, cudaStream_t st) {
   k_tensor_proj_pack<<<148, 256, 0, st>>>(l, pack, off_om);
   return cudaGetLastError() == cudaSuccess ? PSBAX_OK : PSBAX_E_CUDA;
 }
+
+#endif  // PSBAX_TU_API
 
 // Waiting roles back off between probes: in this kernel the producers are NOT the bottleneck, and
 // twenty lanes re-polling mbarriers at full rate starve the MMA issuer's own barrier traffic in
@@ -183,7 +189,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
 
   const int d = lay.d, OS = lay.OS, dp4 = lay.dp4;
   const int kx = tp_kx(d);
-  const int nkb = lay.Kp / TP_TKB;
+  const int nkb_r = lay.nkb_r;              // 32-feature blocks (bf16x3)
+  const int nkb = lay.nkb_r + lay.nkb_k;    // + exact-kernel blocks of KF rows (3xTF32), see layout_blocks()
+  constexpr int KF = TP_TKB / 2;
   const uint32_t STAGE = sl.stage;
   const uint32_t om_split = 32u * (uint32_t)kx * 4u;  // bytes per split image
   const int s0 = blockIdx.y * TN;
@@ -240,18 +248,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     const uint8_t* gW = reinterpret_cast<const uint8_t*>(a.pack + lay.off_tc) + (size_t)blockIdx.y * nkb * TP_WBYTES;
     const uint8_t* gO = reinterpret_cast<const uint8_t*>(a.pack + off_om);
     const uint8_t* gFT = reinterpret_cast<const uint8_t*>(a.pack + lay.off_ft);
-    const uint32_t obytes = tp_obytes(d), ftbytes = (uint32_t)TP_TKB * OS * 4;
+    const uint32_t obytes = tp_obytes(d);
     uint32_t kb = 0, bs = 0, ph = 0;  // block inside the pass; ring stage and its phase
     for (uint32_t it = 0; it < total_blocks; ++it) {
-      const bool has_kernel_rows = lay.np_ > 0 && (int)(kb + 1) * TP_TKB > lay.Lp_ft;  // (no table slot when np_ == 0)
+      const bool kblk = (int)kb >= nkb_r;  // exact-kernel block: [W;V] image (tf32) + its KF table rows, no projection
       TC_TRACE(3, it, 0);
       mbar_wait_hybrid_backoff<200>(&b_empty[bs], ph ^ 1, lane);
       TC_TRACE(3, it, 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(&b_full[bs], TP_WBYTES + obytes + (has_kernel_rows ? ftbytes : 0u));
-        bulk_g2s(sB + bs * STAGE, gW + (size_t)kb * TP_WBYTES, TP_WBYTES, &b_full[bs]);
-        bulk_g2s(sB + bs * STAGE + TP_WBYTES, gO + (size_t)kb * obytes, obytes, &b_full[bs]);
-        if (has_kernel_rows) bulk_g2s(sB + bs * STAGE + sl.ftk, gFT + (size_t)kb * ftbytes, ftbytes, &b_full[bs]);
+        if (kblk) {
+          const uint32_t fb = (uint32_t)KF * OS * 4;
+          mbar_arrive_expect_tx(&b_full[bs], TP_WBYTES + fb);
+          bulk_g2s(sB + bs * STAGE, gW + (size_t)kb * TP_WBYTES, TP_WBYTES, &b_full[bs]);
+          bulk_g2s(sB + bs * STAGE + sl.ftk, gFT + ((size_t)lay.kk0 + (size_t)(kb - nkb_r) * KF) * OS * 4, fb, &b_full[bs]);
+        } else {
+          mbar_arrive_expect_tx(&b_full[bs], TP_WBYTES + obytes);
+          bulk_g2s(sB + bs * STAGE, gW + (size_t)kb * TP_WBYTES, TP_WBYTES, &b_full[bs]);
+          bulk_g2s(sB + bs * STAGE + TP_WBYTES, gO + (size_t)kb * obytes, obytes, &b_full[bs]);
+        }
       }
       __syncwarp();
       if (++kb == (uint32_t)nkb) kb = 0;
@@ -283,8 +297,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       TC_TRACE(0, jt, 4);
       if (elect_one()) {
         const uint64_t oh0 = dO0 + (uint64_t)(bs * stage16), ol0 = oh0 + osplit16;
+        // exact-kernel blocks have no projection: only the barrier protocol runs
 #pragma unroll
-        for (int t = 0; t < TC_TILES; ++t) {
+        for (int t = 0; t < ((int)jkb < nkb_r ? TC_TILES : 0); ++t) {
           const uint32_t dz = tmem + TP_COL_Z + (zb * TC_TILES + t) * 32;
           const uint32_t xh = tmem + TP_COL_X + (t * 2) * 32, xl = xh + 32;
           tc_mma_ts(dz, xh, oh0, IDESC_P, 0u);
@@ -325,6 +340,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       TC_TRACE(0, it, 2);
       if (elect_one()) {
         const uint64_t b10 = dW0 + (uint64_t)(bs * stage16);
+        if ((int)kb >= nkb_r) {
+          // exact-kernel block: KF features as TF32 hi | lo (A columns [0, 16) | [16, 32)), K = 8 per MMA
+          constexpr uint32_t IDESC_K = umma_idesc_tf32(TN);
+          constexpr uint32_t SBO_K = KF * 4 * 8, SPLIT2_K = 8 * SBO_K;
+          const uint64_t k10 = umma_desc_kmajor(smem_u32(sB), 128, SBO_K) + (uint64_t)(bs * stage16);
+#pragma unroll
+          for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+            for (int ks = 0; ks < KF / 8; ++ks) {
+              const uint64_t b1 = k10 + (uint64_t)(ks * 16);
+              const uint64_t b2 = b1 + (uint64_t)(SPLIT2_K >> 4);
+              const uint32_t a1 = tmem + TP_COL_A + (as * TC_TILES + t) * 32 + ks * 8, a2 = a1 + 16;
+              const uint32_t dd = tmem + TP_COL_D + t * TN;
+              tc_mma_ts(dd, a1, b1, IDESC_K, (kb | ks) ? 1u : 0u);
+              tc_mma_ts(dd, a1, b2, IDESC_K, 1u);
+              tc_mma_ts(dd, a2, b1, IDESC_K, 1u);
+            }
+        } else {
 #pragma unroll
         for (int t = 0; t < TC_TILES; ++t)
 #pragma unroll
@@ -337,6 +370,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
             tc_mma_ts_bf16(dd, a1, b2, IDESC_C, 1u);
             tc_mma_ts_bf16(dd, a2, b1, IDESC_C, 1u);
           }
+        }
         tc_commit(&a_empty[as]);
         tc_commit(&b_empty[bs]);
         if (last) tc_commit(d_full);
@@ -400,54 +434,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
         mbar_wait_hybrid_backoff(&z_full[zb], ph, lane);
         tc_fence_after();
         if (warp == 0) TC_TRACE(1, it, 1);
+        const bool kblk = kb >= nkb_r;  // exact-kernel block (KF rows, 3xTF32): no projection arguments to read
         uint32_t z[TC_TILES][8];
+        if (!kblk) {
 #pragma unroll
-        for (int t = 0; t < TC_TILES; ++t) tc_ld8(lane_addr + TP_COL_Z + (zb * TC_TILES + t) * 32 + h * 8, z[t]);
-        tc_wait_ld();
+          for (int t = 0; t < TC_TILES; ++t) tc_ld8(lane_addr + TP_COL_Z + (zb * TC_TILES + t) * 32 + h * 8, z[t]);
+          tc_wait_ld();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&z_empty[zb]);
         if (warp == 0) TC_TRACE(1, it, 2);
-        float v[TC_TILES][8];
-        if (kbase < lay.Lp_ft) {
-          const bool lin = kbase >= lay.Lcos;
-          float arg[TC_TILES][8];
-#pragma unroll
-          for (int t = 0; t < TC_TILES; ++t)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) arg[t][j] = __uint_as_float(z[t][j]);
-          if (!bias_in_x) {  // d % 8 == 0: the bias is not part of the projection
-            const float4 b0 = *reinterpret_cast<const float4*>(sBias + kbase);
-            const float4 b1 = *reinterpret_cast<const float4*>(sBias + kbase + 4);
-            const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        // the two MMA operands of this warp's features: 8 features as bf16 pairs (split 1 | split 2) or,
+        // in an exact-kernel block, 4 features as TF32 (hi | lo) — the same 4 + 4 tensor-memory columns
+        uint32_t s1[TC_TILES][4], s2[TC_TILES][4];
+        if (!kblk) {
+          float v[TC_TILES][8];
+          if (kbase < lay.Lp_ft) {
+            const bool lin = kbase >= lay.Lcos;
+            float arg[TC_TILES][8];
 #pragma unroll
             for (int t = 0; t < TC_TILES; ++t)
 #pragma unroll
-              for (int j = 0; j < 8; ++j) arg[t][j] += bj[j];
+              for (int j = 0; j < 8; ++j) arg[t][j] = __uint_as_float(z[t][j]);
+            if (!bias_in_x) {  // d % 8 == 0: the bias is not part of the projection
+              const float4 b0 = *reinterpret_cast<const float4*>(sBias + kbase);
+              const float4 b1 = *reinterpret_cast<const float4*>(sBias + kbase + 4);
+              const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) arg[t][j] += bj[j];
+            }
+#pragma unroll
+            for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[t][j] = lin ? arg[t][j] : __cosf(arg[t][j]);
+          } else {  // padding rows between the RFF section and the first exact-kernel block (zero weights)
+#pragma unroll
+            for (int t = 0; t < TC_TILES; ++t)
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[t][j] = 0.f;
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&b_empty[bs]);
+          // ---- BF16x3 split ----
 #pragma unroll
           for (int t = 0; t < TC_TILES; ++t)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[t][j] = lin ? arg[t][j] : __cosf(arg[t][j]);
-        } else if (kbase >= lay.Lp_ft + lay.np_) {  // padding rows up to the block size (zero weights)
-#pragma unroll
-          for (int t = 0; t < TC_TILES; ++t)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[t][j] = 0.f;
-        } else {  // exact-kernel features: FFMA path (r^2 as a sum of squared differences)
-          // the block's table rows sit behind the operand images of the same stage (already
-          // landed: the projection MMAs of this block read the stage; the wait returns at once)
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t p1 = cvt_bf16x2(v[t][2 * c + 1], v[t][2 * c]);
+              const uint64_t rr = ffma2(pack2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u)),
+                                        pack2(-1.0f, -1.0f), pack2(v[t][2 * c], v[t][2 * c + 1]));
+              float r0, r1;
+              unpack2(rr, r0, r1);
+              s1[t][c] = p1;
+              s2[t][c] = cvt_bf16x2(r1, r0);
+            }
+        } else {
+          // ---- exact-kernel block: KF = 16 features, 4 per warp (FFMA path: r^2 as a sum of squared
+          // differences), TF32 hi | lo operands ----
+          // the block's table rows sit behind the [W;V] image of the same stage
           mbar_wait_hybrid_backoff(&b_full[bs], bph, lane);
-          const float* ft = reinterpret_cast<const float*>(sB + bs * STAGE + sl.ftk) + (size_t)(h * 8) * OS;
-          float acc[TC_TILES][8];
+          const float* ft = reinterpret_cast<const float*>(sB + bs * STAGE + sl.ftk) + (size_t)(h * 4) * OS;
+          float acc[TC_TILES][4];
           if constexpr (PAIRX) {
             // packed FP32 over the thread's (tile 0, tile 1) rows; inv_ls and the table entry enter as
             // scalar-broadcast operands:  df = x * inv_ls + (-x_t * inv_ls),  acc += df * df
             static_assert(TC_TILES == 2, "row-pair arithmetic");
             const uint64_t* xr = reinterpret_cast<const uint64_t*>(sX) + q * 32 + lane;
-            uint64_t acc2[8];
+            uint64_t acc2[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc2[j] = 0ull;
+            for (int j = 0; j < 4; ++j) acc2[j] = 0ull;
             for (int i0 = 0; i0 < dp4; i0 += 4) {
               uint64_t xa[4];
               float il4[4];
@@ -457,7 +515,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
                 il4[c] = sIl[i0 + c];
               }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < 4; ++j) {
                 const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
                 const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
@@ -468,13 +526,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
               }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) unpack2(acc2[j], acc[0][j], acc[1][j]);
+            for (int j = 0; j < 4; ++j) unpack2(acc2[j], acc[0][j], acc[1][j]);
           } else {
             const float* xs = sX + q * 32 + lane;
 #pragma unroll
             for (int t = 0; t < TC_TILES; ++t)
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+              for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
             for (int i0 = 0; i0 < dp4; i0 += 4) {
               float xa[TC_TILES][4];
 #pragma unroll
@@ -482,7 +540,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
 #pragma unroll
                 for (int c = 0; c < 4; ++c) xa[t][c] = xs[(t * dp4 + i0 + c) * TM] * sIl[i0 + c];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < 4; ++j) {
                 const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
                 const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
@@ -495,25 +553,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
               }
             }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&b_empty[bs]);
 #pragma unroll
-          for (int t = 0; t < TC_TILES; ++t) kernel_profile8(acc[t], v[t], lay.kernel);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&b_empty[bs]);
-        // ---- BF16x3 split, store into the A stage ----
-        uint32_t s1[TC_TILES][4], s2[TC_TILES][4];
+          for (int t = 0; t < TC_TILES; ++t) {
+            float kv[4];
+            kernel_profile_n<4>(acc[t], kv, lay.kernel);
 #pragma unroll
-        for (int t = 0; t < TC_TILES; ++t)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t p1 = cvt_bf16x2(v[t][2 * c + 1], v[t][2 * c]);
-            const uint64_t rr = ffma2(pack2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u)),
-                                      pack2(-1.0f, -1.0f), pack2(v[t][2 * c], v[t][2 * c + 1]));
-            float r0, r1;
-            unpack2(rr, r0, r1);
-            s1[t][c] = p1;
-            s2[t][c] = cvt_bf16x2(r1, r0);
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t hb = __float_as_uint(kv[j]) & 0xffffe000u;
+              s1[t][j] = hb;
+              s2[t][j] = __float_as_uint(kv[j] - __uint_as_float(hb));
+            }
           }
+        }
         if (warp == 0) TC_TRACE(1, it, 3);
         mbar_wait_hybrid_backoff(&a_empty[as], ph ^ 1, lane);
         tc_fence_after();
@@ -603,7 +656,9 @@ int tensor_proj_launch_epi(const KArgs& a, int sms, cudaStream_t st, char* err, 
   return PSBAX_OK;
 }
 
-inline int tensor_proj_launch(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
+int tensor_proj_launch(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen);  // tensor_proj.cu
+#ifdef PSBAX_TU_PROJ
+inline int tensor_proj_launch_impl(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
   // Packed-FP32 exact-kernel rows: measured per instantiation (same box, d = 5 / 10 / 32).  The
   // level-set kernel (register-resident epilogue state, tightest register budget) only gains from
   // d = 13 on (d = 10: 7.78 -> 8.23 ms, d = 32: 3.01 -> 2.87); top-k and values gain from d = 5
@@ -617,6 +672,8 @@ inline int tensor_proj_launch(int epi, const KArgs& a, int sms, cudaStream_t st,
   TP_LAUNCH(EPI_TOPK);
 #undef TP_LAUNCH
 }
+
+#endif
 
 inline int tensor_launch_any(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
   return a.lay.tc_proj ? tensor_proj_launch(epi, a, sms, st, err, errlen) : tensor_launch(epi, a, sms, st, err, errlen);
