@@ -24,7 +24,8 @@
  *    nothing is allocated after psbax_pack_bytes()/psbax_workspace_bytes();
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *    calls are asynchronous with respect to the host;
- *  - re-entrant: no global mutable state besides per-device function attributes.
+ *  - re-entrant: no global mutable state besides per-device function attributes and the calling
+ *    thread's last error message.
  */
 #ifndef PSBAX_B200_H
 #define PSBAX_B200_H
@@ -36,7 +37,7 @@
 extern "C" {
 #endif
 
-#define PSBAX_ABI_VERSION 1
+#define PSBAX_ABI_VERSION 2
 
 enum {
   PSBAX_OK = 0,
@@ -93,9 +94,10 @@ int psbax_version(void);
 /* Copies the calling thread's last error message (NUL-terminated) into buf. */
 int psbax_last_error(char* buf, size_t len);
 
-/* Profiling aid (not used by the product path): when set to a device buffer of at least
- * 4 * 128 * 8 int64, CTA 0 of the tensor-engine kernel records clock64() time stamps of its
- * pipeline stages there; NULL (the default) disables tracing. */
+/* Profiling aid, compiled in only in the trace build of the library (python -m psbax_b200.build
+ * --trace, -DPSBAX_TC_TRACE=1): CTA 0 of the tensor-engine kernel records clock64() time stamps of
+ * its pipeline stages in a device buffer of at least 4 * 128 * 8 int64.  The product build keeps no
+ * such state and returns PSBAX_E_UNSUPPORTED. */
 int psbax_debug_trace_buffer(void* device_buffer);
 
 /* Number of SMs of the current device (sizes persistent grids / workspaces). */
@@ -138,6 +140,33 @@ int psbax_eval_levelset(const psbax_paths_t* paths, const void* pack, const floa
                         int64_t row_offset, float tau, uint32_t* mask, int64_t mask_ld,
                         int64_t* count, float* maxval, int64_t* argmax, void* workspace,
                         size_t workspace_bytes, void* stream);
+
+/* Candidate rows generated on the device instead of read from memory: row r of the call is row
+ * (row_offset + r) of the 'ij'-ordered mesh of `d` axes, first axis slowest — the layout of
+ * reshape_mesh(get_mesh(d, steps)) (src/utils.py:264-286) that demos/level-set.py:40-41 feeds the
+ * level-set algorithm as x_set.  The axis values are read as given (no linspace is recomputed), so
+ * the rows are bit-identical to the float32 mesh the caller would otherwise upload. */
+typedef struct psbax_mesh {
+  int32_t d;            /* number of axes; must equal paths->d, 1 <= d <= 4 */
+  int32_t reserved;
+  int64_t len[4];       /* points per axis */
+  const float* axis[4]; /* DEVICE pointers: axis[i] holds len[i] floats */
+} psbax_mesh_t;
+
+/* psbax_eval_levelset with two options (either may be NULL):
+ *  - mesh: the candidate rows come from a mesh descriptor (then X must be NULL and
+ *    row_offset + N <= prod(len));
+ *  - pooled: [ceil(N/32)] words, bit (i % 32) of pooled[i / 32] = OR over the S paths of the mask bits,
+ *    i.e. candidate i is in at least one path's super-level set: the pool
+ *    gen_posterior_sampling_batch builds from the S outputs
+ *    (src/acquisition_functions/posterior_sampling.py:64-78) without its duplicates.  The call
+ *    zeroes the buffer (asynchronously, on `stream`) before the kernel ORs into it.
+ * mask may be NULL as well: only N/8 bytes then leave the kernel. */
+int psbax_eval_levelset_ex(const psbax_paths_t* paths, const void* pack, const float* X,
+                           const psbax_mesh_t* mesh, int64_t N, int64_t row_offset, float tau,
+                           uint32_t* mask, int64_t mask_ld, uint32_t* pooled, int64_t* count,
+                           float* maxval, int64_t* argmax, void* workspace, size_t workspace_bytes,
+                           void* stream);
 
 /* Fused evaluation + TopK reduction (src/algorithms/topk.py:31-34) for all S
  * paths: out_val[s, 0..k) the k largest f_s values, largest first, ties broken

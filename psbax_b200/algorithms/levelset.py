@@ -86,12 +86,10 @@ class LevelSetEstimator(Algorithm):
         empty (``levelset.py:35-37``)."""
         X = self.device_candidates(paths.device)
         N = X.shape[0]
-        res = paths.levelset(X, self.params.threshold)
-        words = res.mask[0].clone()
-        for s in range(1, paths.S):
-            words |= res.mask[s]
-        shifts = torch.arange(32, device=words.device, dtype=torch.int32)
-        bits = ((words.unsqueeze(1) >> shifts) & 1).bool().reshape(-1)[:N].clone()
+        # the OR over the S masks is formed inside the kernel; the S x N / 8 byte masks are never written
+        res = paths.levelset(X, self.params.threshold, want_mask=False, want_pooled=True)
+        shifts = torch.arange(32, device=res.pooled.device, dtype=torch.int32)
+        bits = ((res.pooled.unsqueeze(1) >> shifts) & 1).bool().reshape(-1)[:N].clone()
         empty = res.count == 0
         if bool(empty.any()):
             bits[res.argmax[empty]] = True

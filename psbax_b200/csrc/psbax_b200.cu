@@ -22,7 +22,9 @@ using namespace psbax;
 namespace {
 
 thread_local char g_err[512] = "";
-long long* g_trace = nullptr;  // profiling aid, see psbax_debug_trace_buffer
+#if defined(PSBAX_TC_TRACE) && PSBAX_TC_TRACE
+long long* g_trace = nullptr;  // trace build only, see psbax_debug_trace_buffer
+#endif
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -153,11 +155,12 @@ struct Prepared {
   int sms;
 };
 
-int prepare(const psbax_paths_t* p, const void* pack, const float* X, int64_t N, Prepared* out) {
+int prepare(const psbax_paths_t* p, const void* pack, const float* X, int64_t N, Prepared* out,
+            bool x_optional = false) {
   int rc = validate(p);
   if (rc) return rc;
   if (!pack) return fail(PSBAX_E_INVALID, "pack is NULL (call psbax_pack first)");
-  if (!X) return fail(PSBAX_E_INVALID, "X is NULL");
+  if (!X && !x_optional) return fail(PSBAX_E_INVALID, "X is NULL");
   if (N < 1) return fail(PSBAX_E_INVALID, "N=%lld must be >= 1", (long long)N);
   if (N > 2147483647LL - TM) return fail(PSBAX_E_UNSUPPORTED, "N=%lld exceeds 2^31 rows per call; shard the candidate set", (long long)N);
   rc = device_sms(&out->sms);
@@ -170,7 +173,9 @@ int prepare(const psbax_paths_t* p, const void* pack, const float* X, int64_t N,
   a.N = N;
   a.ystd = p->y_std;
   a.c0 = (float)((double)p->y_std * (double)p->mean_const + (double)p->y_mean);
+#if defined(PSBAX_TC_TRACE) && PSBAX_TC_TRACE
   a.trace = g_trace;
+#endif
   int gx, gy, nt;
   grid_for(a.lay, N, out->sms, &gx, &gy, &nt);
   a.ntiles = nt;
@@ -192,8 +197,13 @@ int psbax_last_error(char* buf, size_t len) {
 }
 
 int psbax_debug_trace_buffer(void* device_buffer) {
+#if defined(PSBAX_TC_TRACE) && PSBAX_TC_TRACE
   g_trace = static_cast<long long*>(device_buffer);
   return PSBAX_OK;
+#else
+  (void)device_buffer;
+  return fail(PSBAX_E_UNSUPPORTED, "clock traces exist only in the trace build (python -m psbax_b200.build --trace)");
+#endif
 }
 
 int psbax_device_sms(int* sms) {
@@ -241,7 +251,7 @@ int psbax_workspace_bytes(const psbax_paths_t* paths, int64_t N, int32_t k, size
   const Layout l = make_layout(paths);
   int gx, gy, nt;
   grid_for(l, N, sms, &gx, &gy, &nt);
-  if (is_tensor_mode(l.mode)) gx = tensor_parts(l, N, sms);
+  if (is_tensor_mode(l.mode)) gx = l.tc_proj ? sms : tensor_parts(l, N, sms);  // (upper bound for the projection variant's plans)
   const size_t per = (size_t)gx * l.Sp;
   const size_t ls = per * (sizeof(unsigned int) + sizeof(float) + sizeof(int));
   const size_t tk = per * (size_t)(k > 0 ? k : 1) * (sizeof(float) + sizeof(int));
@@ -302,8 +312,17 @@ int psbax_eval_levelset(const psbax_paths_t* paths, const void* pack, const floa
                         int64_t row_offset, float tau, uint32_t* mask, int64_t mask_ld,
                         int64_t* count, float* maxval, int64_t* argmax, void* workspace,
                         size_t workspace_bytes, void* stream) {
+  return psbax_eval_levelset_ex(paths, pack, X, nullptr, N, row_offset, tau, mask, mask_ld, nullptr, count,
+                                maxval, argmax, workspace, workspace_bytes, stream);
+}
+
+int psbax_eval_levelset_ex(const psbax_paths_t* paths, const void* pack, const float* X,
+                           const psbax_mesh_t* mesh, int64_t N, int64_t row_offset, float tau,
+                           uint32_t* mask, int64_t mask_ld, uint32_t* pooled, int64_t* count,
+                           float* maxval, int64_t* argmax, void* workspace, size_t workspace_bytes,
+                           void* stream) {
   Prepared pr;
-  int rc = prepare(paths, pack, X, N, &pr);
+  int rc = prepare(paths, pack, X, N, &pr, mesh != nullptr);
   if (rc) return rc;
   if (mask && mask_ld < (N + 31) / 32)
     return fail(PSBAX_E_INVALID, "mask_ld=%lld < ceil(N/32)=%lld", (long long)mask_ld, (long long)((N + 31) / 32));
@@ -314,16 +333,39 @@ int psbax_eval_levelset(const psbax_paths_t* paths, const void* pack, const floa
     return fail(PSBAX_E_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
   KArgs& a = pr.a;
   const Layout& l = a.lay;
-  const int parts = is_tensor_mode(l.mode) ? tensor_parts(l, N, pr.sms) : (int)pr.grid.x;
+  if (mesh) {
+    if (X) return fail(PSBAX_E_INVALID, "pass either X or a mesh, not both");
+    if (mesh->d != paths->d || mesh->d < 1 || mesh->d > 4)
+      return fail(PSBAX_E_UNSUPPORTED, "mesh needs 1 <= d <= 4 axes and d == paths->d (got %d, paths->d = %d)",
+                  mesh->d, paths->d);
+    if (row_offset < 0) return fail(PSBAX_E_INVALID, "row_offset must be >= 0 in mesh mode");
+    long long total = 1;
+    for (int i = mesh->d - 1; i >= 0; --i) {
+      if (mesh->len[i] < 1 || mesh->len[i] > 2147483647LL || !mesh->axis[i])
+        return fail(PSBAX_E_INVALID, "mesh axis %d: len=%lld, pointer %p", i, (long long)mesh->len[i],
+                    (const void*)mesh->axis[i]);
+      a.mesh_axis[i] = mesh->axis[i];
+      a.mesh_len[i] = (int)mesh->len[i];
+      a.mesh_stride[i] = total;
+      if (total > (1LL << 62) / mesh->len[i]) return fail(PSBAX_E_INVALID, "mesh too large");
+      total *= mesh->len[i];
+    }
+    if (row_offset + N > total)
+      return fail(PSBAX_E_INVALID, "rows [%lld, %lld) exceed the mesh (%lld rows)", (long long)row_offset,
+                  (long long)(row_offset + N), total);
+  }
+  const int parts = is_tensor_mode(l.mode) ? tensor_parts_any(l, N, pr.sms, EPI_LEVELSET, 0) : (int)pr.grid.x;
   const size_t per = (size_t)parts * l.Sp;
   a.row_offset = row_offset;
   a.tau = tau;
   a.mask = mask;
   a.mask_ld = mask_ld;
+  a.pooled = pooled;
   a.p_cnt = static_cast<unsigned int*>(workspace);
   a.p_max = reinterpret_cast<float*>(a.p_cnt + per);
   a.p_arg = reinterpret_cast<int*>(a.p_max + per);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (pooled) CUDA_TRY(cudaMemsetAsync(pooled, 0, (size_t)((N + 31) / 32) * sizeof(uint32_t), st));
   if (is_tensor_mode(l.mode)) rc = tensor_launch_any(EPI_LEVELSET, a, pr.sms, st, g_err, sizeof(g_err));
   else rc = simt_launch(EPI_LEVELSET, a, pr.grid, st, g_err, sizeof(g_err));
   if (rc) return rc;
@@ -350,7 +392,7 @@ int psbax_eval_topk(const psbax_paths_t* paths, const void* pack, const float* X
     return fail(PSBAX_E_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
   KArgs& a = pr.a;
   const Layout& l = a.lay;
-  const int parts = is_tensor_mode(l.mode) ? tensor_parts(l, N, pr.sms) : (int)pr.grid.x;
+  const int parts = is_tensor_mode(l.mode) ? tensor_parts_any(l, N, pr.sms, EPI_TOPK, k) : (int)pr.grid.x;
   const size_t per = (size_t)parts * l.Sp * k;
   a.row_offset = row_offset;
   a.k = k;

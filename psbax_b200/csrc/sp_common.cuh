@@ -101,7 +101,23 @@ struct KArgs {
   float* p_tv;
   int* p_ti;
   long long* trace;  // optional device buffer for clock64 traces (psbax_debug_trace_buffer)
+  // LEVELSET, optional: pooled[w] |= OR over the S samples of the mask words (bit i = row i is in at
+  // least one path's super-level set); zeroed by the caller, combined with atomic ORs
+  uint32_t* pooled;
+  // mesh mode (psbax_eval_levelset_ex): X == NULL and candidate row r is row (row_offset + r) of the
+  // 'ij'-ordered mesh of the axes (first axis slowest), generated on the fly
+  const float* mesh_axis[4];
+  long long mesh_stride[4];
+  int mesh_len[4];
 };
+
+// coordinate i of local candidate row `row`: from X, or generated from the mesh axes
+__device__ __forceinline__ float load_x(const KArgs& a, long long row, int i) {
+  if (a.X != nullptr) return __ldg(a.X + row * a.lay.d + i);
+  const long long g = a.row_offset + row;
+  const int j = (int)((g / a.mesh_stride[i]) % a.mesh_len[i]);
+  return __ldg(a.mesh_axis[i] + j);
+}
 
 // ---------------------------------------------------------------------------------
 // math helpers

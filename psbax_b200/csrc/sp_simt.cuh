@@ -141,6 +141,7 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const float* sOut,
         c += __popc(word);
         if (a.mask != nullptr && lane == 0 && (long long)row0 + g * 32 < N)
           a.mask[(long long)s * a.mask_ld + ((row0 + g * 32) >> 5)] = word;
+        if (a.pooled != nullptr && lane == 0 && word != 0u) atomicOr(a.pooled + ((row0 + g * 32) >> 5), word);
         if (valid && better(y, (int)row, bv, bi)) { bv = y; bi = (int)row; }
       }
 #pragma unroll
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_shared_simt(const __grid_consta
       if constexpr (DP > 0) {
 #pragma unroll
         for (int i = 0; i < DP; ++i) {
-          x[i] = (row < a.N && i < lay.d) ? __ldg(a.X + row * lay.d + i) : 0.f;
+          x[i] = (row < a.N && i < lay.d) ? load_x(a, row, i) : 0.f;
           xs[i] = x[i] * __ldg(IL + i);
         }
       } else {
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_shared_simt(const __grid_consta
         const long long lim = a.N * lay.d;
         for (int idx = tid; idx < TM * lay.d; idx += NTHREADS) {
           const int r = idx / lay.d, i = idx - r * lay.d;
-          sX[i * TM + r] = (base + idx < lim) ? __ldg(a.X + base + idx) : 0.f;
+          sX[i * TM + r] = (base + idx < lim) ? load_x(a, (long long)row0 + r, i) : 0.f;
         }
         for (int idx = tid; idx < TM * (dp4 - lay.d); idx += NTHREADS)
           sX[(lay.d + idx / TM) * TM + (idx % TM)] = 0.f;
@@ -455,14 +456,14 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_persample(const __grid_constant
         const long long row = (long long)row0 + r * 32 + lane;
 #pragma unroll
         for (int i = 0; i < DP; ++i)
-          x[r][i] = (row < a.N && i < lay.d) ? __ldg(a.X + row * lay.d + i) : 0.f;
+          x[r][i] = (row < a.N && i < lay.d) ? load_x(a, row, i) : 0.f;
       }
     } else {
       const long long base = (long long)row0 * lay.d;
       const long long lim = a.N * lay.d;
       for (int idx = tid; idx < TM * lay.d; idx += NTHREADS) {
         const int r = idx / lay.d, i = idx - r * lay.d;
-        sX[i * TM + r] = (base + idx < lim) ? __ldg(a.X + base + idx) : 0.f;
+        sX[i * TM + r] = (base + idx < lim) ? load_x(a, (long long)row0 + r, i) : 0.f;
       }
       for (int idx = tid; idx < TM * (dp4 - lay.d); idx += NTHREADS)
         sX[(lay.d + idx / TM) * TM + (idx % TM)] = 0.f;

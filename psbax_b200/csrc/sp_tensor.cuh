@@ -505,6 +505,7 @@ __device__ __forceinline__ void epilogue_levelset_reg_impl(const KArgs& a, const
   const int warp = tid >> 5, lane = tid & 31;
   const long long N = a.N;
   const bool wr = a.mask != nullptr && lane < TM / 32 && (FULL || (long long)row0 + lane * 32 < N);
+  unsigned int pool = 0u;  // lane g < 4: OR over this warp's samples of row group g's word
 #pragma unroll
   for (int q = 0; q < SPW; ++q) {
     const int sl = warp * SPW + q;
@@ -521,8 +522,12 @@ __device__ __forceinline__ void epilogue_levelset_reg_impl(const KArgs& a, const
       // rows only grow for a given lane, so a tie never replaces the earlier (smaller) index
       if (valid && y > st.bv[q]) { st.bv[q] = y; st.bi[q] = row; }
     }
-    if (wr && s0 + sl < a.lay.S) a.mask[(long long)(s0 + sl) * a.mask_ld + (row0 >> 5) + lane] = mine;
+    if (s0 + sl < a.lay.S) {  // (padding samples evaluate to the constant c0: never part of the pool)
+      if (wr) a.mask[(long long)(s0 + sl) * a.mask_ld + (row0 >> 5) + lane] = mine;
+      pool |= mine;
+    }
   }
+  if (a.pooled != nullptr && lane < TM / 32 && pool != 0u) atomicOr(a.pooled + (row0 >> 5) + lane, pool);
 }
 
 template <int NW>
@@ -758,7 +763,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         const long long lim = a.N * lay.d;
         for (int idx = ptid; idx < TC_TILES * TM * lay.d; idx += PT) {
           const int rr = idx / lay.d, i = idx - rr * lay.d;  // rr in [0, 256)
-          sX[(i * TM + (rr & 127)) * TC_TILES + (rr >> 7)] = (base + idx < lim) ? __ldg(a.X + base + idx) : 0.f;
+          sX[(i * TM + (rr & 127)) * TC_TILES + (rr >> 7)] =
+              (base + idx < lim) ? load_x(a, (long long)pass * TC_TILES * TM + rr, i) : 0.f;
         }
         for (int idx = ptid; idx < TC_TILES * TM * (lay.dp4 - lay.d); idx += PT)
           sX[lay.d * TM * TC_TILES + idx] = 0.f;
@@ -767,8 +773,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         const long long row0 = (long long)pass * TC_TILES * TM + q * 32 + lane, row1 = row0 + TM;
 #pragma unroll
         for (int i = 0; i < DP; ++i) {
-          const float x0 = (row0 < a.N && i < lay.d) ? __ldg(a.X + row0 * lay.d + i) : 0.f;
-          const float x1 = (row1 < a.N && i < lay.d) ? __ldg(a.X + row1 * lay.d + i) : 0.f;
+          const float x0 = (row0 < a.N && i < lay.d) ? load_x(a, row0, i) : 0.f;
+          const float x1 = (row1 < a.N && i < lay.d) ? load_x(a, row1, i) : 0.f;
           xp[i] = pack2(x0, x1);
         }
       }

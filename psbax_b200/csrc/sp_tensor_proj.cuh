@@ -14,9 +14,16 @@
 //
 // Warps: 0-15 producers, 16-19 epilogue, 20 contraction issuer, 21 loader, 22 TMEM allocator,
 // 23 projection issuer (it runs up to two blocks ahead of the producers: Z is double-buffered).
-// Tensor-memory columns: D[tile] 0..127 (single-buffered: both tiles are drained to two shared
-// staging tiles before the reduction runs) | X[tile][split] 128..255 | Z[buf][tile] 256..383 |
-// A[stage][tile] 384..511.
+//
+// Two shapes of a CTA pass (template parameter NCH = sample chunks of 64 per CTA):
+//   NCH = 1 (S <= 64)  : TWO 128-row tiles x 64 samples.  Tensor-memory columns: D[tile] 0..127
+//                        (single-buffered: both tiles are drained to two shared staging tiles before
+//                        the reduction runs) | X[tile][split] 128..255 | Z[buf][tile] 256..383 |
+//                        A[stage][tile] 384..511 (2 stages).
+//   NCH = 2, 4 (S > 64): ONE 128-row tile x NCH * 64 samples: every feature of a candidate is
+//                        generated once and contracted with all the chunks' [W;V] images (before: one
+//                        CTA column per chunk, i.e. cos / kernel profiles evaluated S / 64 times).
+//                        D[chunk] 0..NCH*64 | X[split] 64 | Z[buf] 64 | A[stage] 32 each, 4 stages.
 #pragma once
 #include "sp_tensor.cuh"
 
@@ -27,8 +34,19 @@ constexpr int TP_AUTO_MIN_D = 5;  // AUTO uses the projection variant from this 
 constexpr int TP_NSB_MAX = 8, TP_NSB_MIN = 3;  // operand ring depth: as deep as shared memory allows
 constexpr int TP_WARP_PROJ = TC_WARP_MMA + 3;  // the otherwise idle fourth service warp
 static_assert(TP_WARP_PROJ * 32 < TC_THREADS, "projection issuer warp");
-constexpr int TP_COL_D = 0, TP_COL_X = 128, TP_COL_Z = 256, TP_COL_A = 384;
 constexpr int TP_TKB = 32;
+// tensor-memory map of a pass shape
+template <int NCH>
+struct TpCols {
+  static constexpr int TILES = NCH == 1 ? 2 : 1;
+  static constexpr int D = 0;
+  static constexpr int X = NCH * TILES * TN;          // behind the accumulators
+  static constexpr int Z = X + TILES * 2 * 32;        // X: [tile][split] of 32 columns
+  static constexpr int A = Z + 2 * TILES * 32;        // Z: [buf][tile] of 32 columns
+  static constexpr int NSA_FIT = (512 - A) / (TILES * 32);
+  static constexpr int NSA = NSA_FIT > 4 ? 4 : NSA_FIT;  // A ring depth (a power of two)
+  static_assert(NSA == 2 || NSA == 4, "A ring depth");
+};
 constexpr int TP_WBYTES = 128 * TP_TKB * 2;  // bf16 [W;V] image of a block: 8 KB
 
 // K extent of the projection.  The bias rides as an extra column of X_aug (= 1) when the padding
@@ -39,26 +57,29 @@ __host__ __device__ inline int tp_kx(int d) { return tp_bias_in_x(d) ? round_up(
 __host__ __device__ inline uint32_t tp_obytes(int d) { return 2u * 32u * (uint32_t)tp_kx(d) * 4u; }  // hi + lo image
 
 struct TpSmem {
-  // `b`: ring of `nsb` stages = [W;V] image | Omega_aug images | the block's 32 rows of the feature
+  // `b`: ring of `nsb` stages = nch [W;V] images | Omega_aug images | the block's rows of the feature
   // table (only when the problem has exact-kernel rows; copied only for blocks that contain them)
-  uint32_t b, stage, nsb, ftk, x, out, state, il, bias, bars, total;
+  uint32_t b, stage, nsb, ftk, x, out, state, state_stride, il, bias, bars, total;
 };
-__host__ __device__ inline TpSmem tp_smem_layout(const Layout& l, int epi, int k) {
+__host__ __device__ inline TpSmem tp_smem_layout(const Layout& l, int epi, int k, int nch = 1) {
   TpSmem s{};
-  s.ftk = TP_WBYTES + tp_obytes(l.d);  // offset of the table block inside a stage
+  const uint32_t tiles = nch == 1 ? 2u : 1u;
+  s.ftk = (uint32_t)nch * TP_WBYTES + tp_obytes(l.d);  // offset of the table block inside a stage
   s.stage = s.ftk + (l.np_ > 0 ? (uint32_t)(TP_TKB / 2) * l.OS * 4 : 0u);  // + the 16 table rows of an exact-kernel block
+  s.state_stride = (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;  // reduction state of one sample chunk
   // everything but the ring first; the ring takes what is left (a stage is released only after
   // its contraction completes and a bulk copy takes ~2000 cycles, so depth 4 starved the issuers)
-  const uint32_t fixed = (l.n > 0 ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u) + TC_TILES * TN * OUT_LD * 4 +
-                         (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4 + (uint32_t)round_up(l.dp4, 4) * 4 +
+  const uint32_t xbytes = l.n > 0 ? tiles * l.dp4 * TM * 4 : 0u;
+  const uint32_t obytes = tiles * TN * OUT_LD * 4;  // staging: both tiles (NCH = 1) / one chunk at a time
+  const uint32_t fixed = xbytes + obytes + (uint32_t)nch * s.state_stride + (uint32_t)round_up(l.dp4, 4) * 4 +
                          (tp_bias_in_x(l.d) ? 0u : (uint32_t)l.Kp * 4) + 16 + 40 * 8;
   uint32_t nsb = fixed < 227u * 1024u ? (227u * 1024u - fixed) / s.stage : 0u;
   s.nsb = nsb > (uint32_t)TP_NSB_MAX ? (uint32_t)TP_NSB_MAX : nsb;
   uint32_t o = 0;
   s.b = o;     o += s.nsb * s.stage;
-  s.x = o;     o += l.n > 0 ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u;  // x tile for the kernel rows
-  s.out = o;   o += TC_TILES * TN * OUT_LD * 4;                       // two staging tiles
-  s.state = o; o += (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;
+  s.x = o;     o += xbytes;                                            // x tile for the kernel rows
+  s.out = o;   o += obytes;
+  s.state = o; o += (uint32_t)nch * s.state_stride;
   s.il = o;    o += (uint32_t)round_up(l.dp4, 4) * 4;
   s.bias = o;  o += tp_bias_in_x(l.d) ? 0u : (uint32_t)l.Kp * 4;       // per-feature bias (d % 8 == 0)
   o = (o + 15) / 16 * 16;
@@ -89,6 +110,35 @@ inline bool tensor_proj_supported(const psbax_paths_t* p) {
   layout_blocks(l);
   return tp_supported(l);
 }
+// Pass shape and grid of a launch.  Sample chunks per CTA: 1 (S <= 64: two row tiles per pass), else
+// 2 or 4 with one row tile per pass, as many as shared memory allows for this reduction (the
+// top-k lists of every chunk live in shared memory); gy CTA columns cover the chunks, gx * gy <= #SM
+// (one wave of persistent CTAs).
+struct TpPlan { int nch, tiles, gx, gy; };
+inline TpPlan tp_plan(const Layout& l, long long N, int sms, int epi, int k) {
+  const int chunks = l.Sp / TN;
+  int nch = chunks == 1 ? 1 : (chunks == 2 ? 2 : 4);
+  while (nch > 1) {
+    const TpSmem sl = tp_smem_layout(l, epi, k, nch);
+    if (sl.nsb >= (uint32_t)TP_NSB_MIN && sl.total <= TC_SMEM_MAX) break;
+    nch /= 2;
+  }
+  TpPlan p{};
+  p.nch = nch;
+  p.tiles = nch == 1 ? 2 : 1;
+  p.gy = (chunks + nch - 1) / nch;
+  const long long nt = (N + p.tiles * TM - 1) / (p.tiles * TM);
+  long long gx = sms / p.gy;
+  if (gx > nt) gx = nt;
+  if (gx < 1) gx = 1;
+  p.gx = (int)gx;
+  return p;
+}
+// number of per-CTA partial results of a launch (rows of the [parts][Sp] workspace arrays)
+inline int tensor_parts_any(const Layout& l, long long N, int sms, int epi, int k) {
+  return l.tc_proj ? tp_plan(l, N, sms, epi, k).gx : tensor_parts(l, N, sms);
+}
+
 // floats appended to the tensor pack: one (hi | lo) Omega_aug image per 32-feature block
 __host__ __device__ inline size_t tp_pack_floats(const Layout& l) { return (size_t)(l.nkb_r + l.nkb_k) * (tp_obytes(l.d) / 4); }
 
@@ -160,31 +210,34 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
-template <int EPI, bool PAIRX>
+template <int EPI, bool PAIRX, int NCH>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_constant__ KArgs a, size_t off_om) {
   using C = TcCfg<true, true>;  // BF16x3 contraction with 32-feature blocks
+  using M = TpCols<NCH>;        // tensor-memory map
+  constexpr int TILES = M::TILES;
+  constexpr int NSA = M::NSA;
+  static_assert(!(PAIRX && TILES != 2), "the packed-FP32 kernel rows pair the two row tiles of a pass");
   extern __shared__ __align__(128) uint8_t tp_smem[];
   uint8_t* const smem = tp_smem;
   const Layout& lay = a.lay;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const TpSmem sl = tp_smem_layout(lay, EPI, a.k);
+  const TpSmem sl = tp_smem_layout(lay, EPI, a.k, NCH);
   uint8_t* sB = smem + sl.b;
   float* sX = reinterpret_cast<float*>(smem + sl.x);
   float* sOut = reinterpret_cast<float*>(smem + sl.out);
-  float* sState = reinterpret_cast<float*>(smem + sl.state);
   float* sIl = reinterpret_cast<float*>(smem + sl.il);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
   uint64_t* b_full = bars;         // [8]
   uint64_t* b_empty = bars + 8;    // [8]
-  uint64_t* a_full = bars + 16;    // [2]
-  uint64_t* a_empty = bars + 18;   // [2]
-  uint64_t* z_full = bars + 20;    // [2]
-  uint64_t* z_empty = bars + 22;   // [2]
-  uint64_t* x_full = bars + 24;
-  uint64_t* x_empty = bars + 25;
-  uint64_t* d_full = bars + 26;
-  uint64_t* d_empty = bars + 27;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* a_full = bars + 16;    // [4]
+  uint64_t* a_empty = bars + 20;   // [4]
+  uint64_t* z_full = bars + 24;    // [2]
+  uint64_t* z_empty = bars + 26;   // [2]
+  uint64_t* x_full = bars + 28;
+  uint64_t* x_empty = bars + 29;
+  uint64_t* d_full = bars + 30;
+  uint64_t* d_empty = bars + 31;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 32);
   const uint32_t NSB = sl.nsb;
 
   const int d = lay.d, OS = lay.OS, dp4 = lay.dp4;
@@ -194,11 +247,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   constexpr int KF = TP_TKB / 2;
   const uint32_t STAGE = sl.stage;
   const uint32_t om_split = 32u * (uint32_t)kx * 4u;  // bytes per split image
-  const int s0 = blockIdx.y * TN;
-  const int npass = (a.ntiles + TC_TILES - 1) / TC_TILES;
+  const int chunk0 = blockIdx.y * NCH;                 // first sample chunk of this CTA
+  const int s0 = chunk0 * TN;
+  const int nch = min(NCH, lay.Sp / TN - chunk0);      // chunks that exist (the last CTA column may have fewer)
+  const int npass = (a.ntiles + TILES - 1) / TILES;
   int t0, t1;
   tc_tile_range(npass, gridDim.x, blockIdx.x, &t0, &t1);
-  const EpiSmem e = epi_carve(sState, EPI, a.k);
+  EpiSmem e[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) e[c] = epi_carve(reinterpret_cast<float*>(smem + sl.state + c * sl.state_stride), EPI, a.k);
 
   for (int i = tid; i < round_up(dp4, 4); i += TC_THREADS) sIl[i] = __ldg(a.pack + lay.off_invls + i);
   // x tile of the exact-kernel rows: [i][row] (tile 0, tile 1) pairs for the packed-FP32 path, else
@@ -206,9 +263,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   // 80-register cap the mere presence of the second path cost the cos path 10 % (spills).
   constexpr bool pairx = PAIRX;
   if (lay.n > 0)  // padding dimensions d..dp4-1 are read (times inv_ls = 0) but never refilled
-    for (int i = tid; i < TC_TILES * (dp4 - d) * TM; i += TC_THREADS) {
+    for (int i = tid; i < TILES * (dp4 - d) * TM; i += TC_THREADS) {
       if (pairx) {
-        sX[d * TM * TC_TILES + i] = 0.f;
+        sX[d * TM * TILES + i] = 0.f;
       } else {
         const int t = i / ((dp4 - d) * TM), r = i % ((dp4 - d) * TM);
         sX[(t * dp4 + d) * TM + r] = 0.f;
@@ -222,10 +279,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   if (tid == 0) {
     // the producers read the streamed table block, so they release the stage too
     for (int i = 0; i < TP_NSB_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1 + TC_NPROD); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], TC_NPROD); mbar_init(&a_empty[i], 1);
-      mbar_init(&z_full[i], 1);        mbar_init(&z_empty[i], TC_NPROD);
-    }
+    for (int i = 0; i < NSA; ++i) { mbar_init(&a_full[i], TC_NPROD); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], TC_NPROD); }
     mbar_init(x_full, TC_NPROD); mbar_init(x_empty, 1);
     mbar_init(d_full, 1);        mbar_init(d_empty, TC_NEPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -236,7 +291,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_NEPI) epi_init(e, EPI, a.k, tid - TC_EPI_WARP0 * 32, TC_NEPI * 32);
+  if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_NEPI) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) epi_init(e[c], EPI, a.k, tid - TC_EPI_WARP0 * 32, TC_NEPI * 32);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -244,28 +302,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   const uint32_t total_blocks = (uint32_t)(t1 - t0) * (uint32_t)nkb;
 
   if (warp == TC_WARP_LOAD) {
-    // ================= loader: [W;V] image + Omega_aug images of each block =================
-    const uint8_t* gW = reinterpret_cast<const uint8_t*>(a.pack + lay.off_tc) + (size_t)blockIdx.y * nkb * TP_WBYTES;
+    // ================= loader: the chunks' [W;V] images + Omega_aug images of each block =================
+    const uint8_t* gW = reinterpret_cast<const uint8_t*>(a.pack + lay.off_tc) + (size_t)chunk0 * nkb * TP_WBYTES;
     const uint8_t* gO = reinterpret_cast<const uint8_t*>(a.pack + off_om);
     const uint8_t* gFT = reinterpret_cast<const uint8_t*>(a.pack + lay.off_ft);
     const uint32_t obytes = tp_obytes(d);
+    const uint32_t wbytes = (uint32_t)nch * TP_WBYTES;
     uint32_t kb = 0, bs = 0, ph = 0;  // block inside the pass; ring stage and its phase
     for (uint32_t it = 0; it < total_blocks; ++it) {
-      const bool kblk = (int)kb >= nkb_r;  // exact-kernel block: [W;V] image (tf32) + its KF table rows, no projection
+      const bool kblk = (int)kb >= nkb_r;  // exact-kernel block: [W;V] images (tf32) + its KF table rows, no projection
       TC_TRACE(3, it, 0);
       mbar_wait_hybrid_backoff<200>(&b_empty[bs], ph ^ 1, lane);
       TC_TRACE(3, it, 1);
       if (elect_one()) {
-        if (kblk) {
-          const uint32_t fb = (uint32_t)KF * OS * 4;
-          mbar_arrive_expect_tx(&b_full[bs], TP_WBYTES + fb);
-          bulk_g2s(sB + bs * STAGE, gW + (size_t)kb * TP_WBYTES, TP_WBYTES, &b_full[bs]);
+        const uint32_t fb = (uint32_t)KF * OS * 4;
+        mbar_arrive_expect_tx(&b_full[bs], wbytes + (kblk ? fb : obytes));
+        for (int c = 0; c < nch; ++c)  // image (chunk0 + c, kb)
+          bulk_g2s(sB + bs * STAGE + c * TP_WBYTES, gW + ((size_t)c * nkb + kb) * TP_WBYTES, TP_WBYTES, &b_full[bs]);
+        if (kblk)
           bulk_g2s(sB + bs * STAGE + sl.ftk, gFT + ((size_t)lay.kk0 + (size_t)(kb - nkb_r) * KF) * OS * 4, fb, &b_full[bs]);
-        } else {
-          mbar_arrive_expect_tx(&b_full[bs], TP_WBYTES + obytes);
-          bulk_g2s(sB + bs * STAGE, gW + (size_t)kb * TP_WBYTES, TP_WBYTES, &b_full[bs]);
-          bulk_g2s(sB + bs * STAGE + TP_WBYTES, gO + (size_t)kb * obytes, obytes, &b_full[bs]);
-        }
+        else
+          bulk_g2s(sB + bs * STAGE + NCH * TP_WBYTES, gO + (size_t)kb * obytes, obytes, &b_full[bs]);
       }
       __syncwarp();
       if (++kb == (uint32_t)nkb) kb = 0;
@@ -282,7 +339,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     constexpr uint32_t IDESC_P = umma_idesc_tf32(32);
     const uint32_t sbo_o = (uint32_t)(kx / 4) * 128u;
     // the 14-bit start-address field counts 16-byte units; stage offsets never carry out of it
-    const uint64_t dO0 = umma_desc_kmajor(smem_u32(sB) + TP_WBYTES, 128, sbo_o);
+    const uint64_t dO0 = umma_desc_kmajor(smem_u32(sB) + NCH * TP_WBYTES, 128, sbo_o);
     const uint32_t stage16 = STAGE >> 4, osplit16 = om_split >> 4;
     const int nks = kx / 8;
     const uint32_t nkb1 = (uint32_t)nkb - 1;
@@ -299,9 +356,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
         const uint64_t oh0 = dO0 + (uint64_t)(bs * stage16), ol0 = oh0 + osplit16;
         // exact-kernel blocks have no projection: only the barrier protocol runs
 #pragma unroll
-        for (int t = 0; t < ((int)jkb < nkb_r ? TC_TILES : 0); ++t) {
-          const uint32_t dz = tmem + TP_COL_Z + (zb * TC_TILES + t) * 32;
-          const uint32_t xh = tmem + TP_COL_X + (t * 2) * 32, xl = xh + 32;
+        for (int t = 0; t < ((int)jkb < nkb_r ? TILES : 0); ++t) {
+          const uint32_t dz = tmem + M::Z + (zb * TILES + t) * 32;
+          const uint32_t xh = tmem + M::X + (t * 2) * 32, xl = xh + 32;
           tc_mma_ts(dz, xh, oh0, IDESC_P, 0u);
           tc_mma_ts(dz, xh, ol0, IDESC_P, 1u);
           tc_mma_ts(dz, xl, oh0, IDESC_P, 1u);
@@ -322,7 +379,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       if (++bs == NSB) { bs = 0; bph ^= 1; }
     }
   } else if (warp == TC_WARP_MMA) {
-    // ================= contraction issuer: D[tile] += A(block it) * [W;V](block it)^T =================
+    // ================= contraction issuer: D[chunk][tile] += A(block it) * [W;V](chunk, block it)^T =================
     constexpr uint32_t IDESC_C = umma_idesc_bf16(TN);
     const uint64_t dW0 = umma_desc_kmajor(smem_u32(sB), 128, C::B_SBO);
     const uint32_t stage16 = STAGE >> 4;
@@ -330,11 +387,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     uint32_t kb = 0, pl = 0, bs = 0, bph = 0;
     for (uint32_t it = 0; it < total_blocks; ++it) {
       const bool last = kb == nkb1;
-      const uint32_t as = it & 1;
+      const uint32_t as = it % NSA;
       TC_TRACE(0, it, 0);
       if (kb == 0) mbar_wait(d_empty, (pl & 1) ^ 1);
       mbar_wait(&b_full[bs], bph);  // long complete (the projection of this block read the stage); acquire only
-      mbar_wait(&a_full[as], (it >> 1) & 1);
+      mbar_wait(&a_full[as], (it / NSA) & 1);
       __syncwarp();
       tc_fence_after();
       TC_TRACE(0, it, 2);
@@ -345,31 +402,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           constexpr uint32_t IDESC_K = umma_idesc_tf32(TN);
           constexpr uint32_t SBO_K = KF * 4 * 8, SPLIT2_K = 8 * SBO_K;
           const uint64_t k10 = umma_desc_kmajor(smem_u32(sB), 128, SBO_K) + (uint64_t)(bs * stage16);
+#pragma unroll 1
+          for (int c = 0; c < nch; ++c)
 #pragma unroll
-          for (int t = 0; t < TC_TILES; ++t)
+            for (int t = 0; t < TILES; ++t)
 #pragma unroll
-            for (int ks = 0; ks < KF / 8; ++ks) {
-              const uint64_t b1 = k10 + (uint64_t)(ks * 16);
-              const uint64_t b2 = b1 + (uint64_t)(SPLIT2_K >> 4);
-              const uint32_t a1 = tmem + TP_COL_A + (as * TC_TILES + t) * 32 + ks * 8, a2 = a1 + 16;
-              const uint32_t dd = tmem + TP_COL_D + t * TN;
-              tc_mma_ts(dd, a1, b1, IDESC_K, (kb | ks) ? 1u : 0u);
-              tc_mma_ts(dd, a1, b2, IDESC_K, 1u);
-              tc_mma_ts(dd, a2, b1, IDESC_K, 1u);
-            }
+              for (int ks = 0; ks < KF / 8; ++ks) {
+                const uint64_t b1 = k10 + (uint64_t)(c * (TP_WBYTES >> 4) + ks * 16);
+                const uint64_t b2 = b1 + (uint64_t)(SPLIT2_K >> 4);
+                const uint32_t a1 = tmem + M::A + (as * TILES + t) * 32 + ks * 8, a2 = a1 + 16;
+                const uint32_t dd = tmem + M::D + (c * TILES + t) * TN;
+                tc_mma_ts(dd, a1, b1, IDESC_K, (kb | ks) ? 1u : 0u);
+                tc_mma_ts(dd, a1, b2, IDESC_K, 1u);
+                tc_mma_ts(dd, a2, b1, IDESC_K, 1u);
+              }
         } else {
+#pragma unroll 1
+          for (int c = 0; c < nch; ++c)
 #pragma unroll
-        for (int t = 0; t < TC_TILES; ++t)
+            for (int t = 0; t < TILES; ++t)
 #pragma unroll
-          for (int ks = 0; ks < C::KSTEPS; ++ks) {
-            const uint64_t b1 = b10 + (uint64_t)(ks * (C::B_KSTEP >> 4));
-            const uint64_t b2 = b1 + (uint64_t)(C::B_SPLIT2 >> 4);
-            const uint32_t a1 = tmem + TP_COL_A + (as * TC_TILES + t) * 32 + ks * 8, a2 = a1 + 16;
-            const uint32_t dd = tmem + TP_COL_D + t * TN;
-            tc_mma_ts_bf16(dd, a1, b1, IDESC_C, (kb | ks) ? 1u : 0u);
-            tc_mma_ts_bf16(dd, a1, b2, IDESC_C, 1u);
-            tc_mma_ts_bf16(dd, a2, b1, IDESC_C, 1u);
-          }
+              for (int ks = 0; ks < C::KSTEPS; ++ks) {
+                const uint64_t b1 = b10 + (uint64_t)(c * (TP_WBYTES >> 4) + ks * (C::B_KSTEP >> 4));
+                const uint64_t b2 = b1 + (uint64_t)(C::B_SPLIT2 >> 4);
+                const uint32_t a1 = tmem + M::A + (as * TILES + t) * 32 + ks * 8, a2 = a1 + 16;
+                const uint32_t dd = tmem + M::D + (c * TILES + t) * TN;
+                tc_mma_ts_bf16(dd, a1, b1, IDESC_C, (kb | ks) ? 1u : 0u);
+                tc_mma_ts_bf16(dd, a1, b2, IDESC_C, 1u);
+                tc_mma_ts_bf16(dd, a2, b1, IDESC_C, 1u);
+              }
         }
         tc_commit(&a_empty[as]);
         tc_commit(&b_empty[bs]);
@@ -392,9 +453,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       // ---- X operand of this pass: warp h writes tile (h >> 1), split (h & 1) of its rows ----
       mbar_wait_hybrid_backoff(x_empty, (pl & 1) ^ 1, lane);
       tc_fence_after();
-      {
+      if (h < 2 * TILES) {
         const int t = h >> 1, split = h & 1;
-        const long long row = ((long long)pass * TC_TILES + t) * TM + q * 32 + lane;
+        const long long row = ((long long)pass * TILES + t) * TM + q * 32 + lane;
         const float* xr = a.X + row * d;
         const bool ok = row < a.N;
         for (int c = 0; c < kx / 8; ++c) {
@@ -406,18 +467,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
             const uint32_t hb = (__float_as_uint(xv) + 0x1000u) & 0xffffe000u;  // round to TF32: |lo| <= 2^-11 |x|
             v[j] = split == 0 ? hb : __float_as_uint(xv - __uint_as_float(hb));
           }
-          tc_st8(lane_addr + TP_COL_X + (t * 2 + split) * 32 + c * 8, v);
+          tc_st8(lane_addr + M::X + (t * 2 + split) * 32 + c * 8, v);
         }
         tc_wait_st();
       }
       if (lay.n > 0) {  // plain x tile for the exact-kernel features
         asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
-        const long long base = (long long)pass * TC_TILES * TM * d;
+        const long long base = (long long)pass * TILES * TM * d;
         const long long lim = a.N * d;
-        for (int idx = ptid; idx < TC_TILES * TM * d; idx += PT) {
+        for (int idx = ptid; idx < TILES * TM * d; idx += PT) {
           const int rr = idx / d, i = idx - rr * d;
           const float xv = (base + idx < lim) ? __ldg(a.X + base + idx) : 0.f;
-          if (pairx) sX[(i * TM + (rr & 127)) * TC_TILES + (rr >> 7)] = xv;  // one LDS.64 feeds a packed FFMA2
+          if (pairx) sX[(i * TM + (rr & 127)) * TILES + (rr >> 7)] = xv;  // one LDS.64 feeds a packed FFMA2
           else sX[((rr >> 7) * dp4 + i) * TM + (rr & 127)] = xv;
         }
         asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
@@ -427,18 +488,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       if (lane == 0) mbar_arrive(x_full);
 
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const uint32_t as = it & 1, zb = it & 1, ph = (it >> 1) & 1;
+        const uint32_t as = it % NSA, aph = (it / NSA) & 1, zb = it & 1, zph = (it >> 1) & 1;
         const int kbase = kb * TP_TKB + h * 8;
-        // ---- arguments of this warp's 8 features x 2 tiles from the projection ----
+        // ---- arguments of this warp's 8 features x TILES tiles from the projection ----
         if (warp == 0) TC_TRACE(1, it, 0);
-        mbar_wait_hybrid_backoff(&z_full[zb], ph, lane);
+        mbar_wait_hybrid_backoff(&z_full[zb], zph, lane);
         tc_fence_after();
         if (warp == 0) TC_TRACE(1, it, 1);
         const bool kblk = kb >= nkb_r;  // exact-kernel block (KF rows, 3xTF32): no projection arguments to read
-        uint32_t z[TC_TILES][8];
+        uint32_t z[TILES][8];
         if (!kblk) {
 #pragma unroll
-          for (int t = 0; t < TC_TILES; ++t) tc_ld8(lane_addr + TP_COL_Z + (zb * TC_TILES + t) * 32 + h * 8, z[t]);
+          for (int t = 0; t < TILES; ++t) tc_ld8(lane_addr + M::Z + (zb * TILES + t) * 32 + h * 8, z[t]);
           tc_wait_ld();
         }
         tc_fence_before();
@@ -447,14 +508,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
         if (warp == 0) TC_TRACE(1, it, 2);
         // the two MMA operands of this warp's features: 8 features as bf16 pairs (split 1 | split 2) or,
         // in an exact-kernel block, 4 features as TF32 (hi | lo) — the same 4 + 4 tensor-memory columns
-        uint32_t s1[TC_TILES][4], s2[TC_TILES][4];
+        uint32_t s1[TILES][4], s2[TILES][4];
         if (!kblk) {
-          float v[TC_TILES][8];
+          float v[TILES][8];
           if (kbase < lay.Lp_ft) {
             const bool lin = kbase >= lay.Lcos;
-            float arg[TC_TILES][8];
+            float arg[TILES][8];
 #pragma unroll
-            for (int t = 0; t < TC_TILES; ++t)
+            for (int t = 0; t < TILES; ++t)
 #pragma unroll
               for (int j = 0; j < 8; ++j) arg[t][j] = __uint_as_float(z[t][j]);
             if (!bias_in_x) {  // d % 8 == 0: the bias is not part of the projection
@@ -462,17 +523,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
               const float4 b1 = *reinterpret_cast<const float4*>(sBias + kbase + 4);
               const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-              for (int t = 0; t < TC_TILES; ++t)
+              for (int t = 0; t < TILES; ++t)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) arg[t][j] += bj[j];
             }
 #pragma unroll
-            for (int t = 0; t < TC_TILES; ++t)
+            for (int t = 0; t < TILES; ++t)
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[t][j] = lin ? arg[t][j] : __cosf(arg[t][j]);
           } else {  // padding rows between the RFF section and the first exact-kernel block (zero weights)
 #pragma unroll
-            for (int t = 0; t < TC_TILES; ++t)
+            for (int t = 0; t < TILES; ++t)
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[t][j] = 0.f;
           }
@@ -480,7 +541,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           if (lane == 0) mbar_arrive(&b_empty[bs]);
           // ---- BF16x3 split ----
 #pragma unroll
-          for (int t = 0; t < TC_TILES; ++t)
+          for (int t = 0; t < TILES; ++t)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const uint32_t p1 = cvt_bf16x2(v[t][2 * c + 1], v[t][2 * c]);
@@ -494,14 +555,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
         } else {
           // ---- exact-kernel block: KF = 16 features, 4 per warp (FFMA path: r^2 as a sum of squared
           // differences), TF32 hi | lo operands ----
-          // the block's table rows sit behind the [W;V] image of the same stage
+          // the block's table rows sit behind the [W;V] images of the same stage
           mbar_wait_hybrid_backoff(&b_full[bs], bph, lane);
           const float* ft = reinterpret_cast<const float*>(sB + bs * STAGE + sl.ftk) + (size_t)(h * 4) * OS;
-          float acc[TC_TILES][4];
+          float acc[TILES][4];
           if constexpr (PAIRX) {
             // packed FP32 over the thread's (tile 0, tile 1) rows; inv_ls and the table entry enter as
             // scalar-broadcast operands:  df = x * inv_ls + (-x_t * inv_ls),  acc += df * df
-            static_assert(TC_TILES == 2, "row-pair arithmetic");
             const uint64_t* xr = reinterpret_cast<const uint64_t*>(sX) + q * 32 + lane;
             uint64_t acc2[4];
 #pragma unroll
@@ -526,17 +586,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
               }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) unpack2(acc2[j], acc[0][j], acc[1][j]);
+            for (int j = 0; j < 4; ++j) unpack2(acc2[j], acc[0][j], acc[TILES - 1][j]);
+          } else if constexpr (TILES == 1) {
+            // one row per thread: packed FP32 over PAIRS OF FEATURES.  df = (x * inv_ls) + (-x_t * inv_ls)
+            // for features (2p, 2p + 1) at once; the scaled coordinate is broadcast into both halves.
+            const float* xs = sX + q * 32 + lane;
+            uint64_t acc2[2] = {0ull, 0ull};
+            for (int i0 = 0; i0 < dp4; i0 += 4) {
+              uint64_t xb[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const float xv = xs[(i0 + c) * TM] * sIl[i0 + c];
+                xb[c] = pack2(xv, xv);
+              }
+#pragma unroll
+              for (int pj = 0; pj < 2; ++pj) {
+                const float4 wa = *reinterpret_cast<const float4*>(ft + (2 * pj) * OS + i0);
+                const float4 wb = *reinterpret_cast<const float4*>(ft + (2 * pj + 1) * OS + i0);
+                const float wa4[4] = {wa.x, wa.y, wa.z, wa.w}, wb4[4] = {wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const uint64_t df = ffma2(xb[c], pack2(1.0f, 1.0f), pack2(wa4[c], wb4[c]));
+                  acc2[pj] = ffma2(df, df, acc2[pj]);
+                }
+              }
+            }
+            unpack2(acc2[0], acc[0][0], acc[0][1]);
+            unpack2(acc2[1], acc[0][2], acc[0][3]);
           } else {
             const float* xs = sX + q * 32 + lane;
 #pragma unroll
-            for (int t = 0; t < TC_TILES; ++t)
+            for (int t = 0; t < TILES; ++t)
 #pragma unroll
               for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
             for (int i0 = 0; i0 < dp4; i0 += 4) {
-              float xa[TC_TILES][4];
+              float xa[TILES][4];
 #pragma unroll
-              for (int t = 0; t < TC_TILES; ++t)
+              for (int t = 0; t < TILES; ++t)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) xa[t][c] = xs[(t * dp4 + i0 + c) * TM] * sIl[i0 + c];
 #pragma unroll
@@ -544,7 +630,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
                 const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
                 const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                for (int t = 0; t < TC_TILES; ++t)
+                for (int t = 0; t < TILES; ++t)
 #pragma unroll
                   for (int c = 0; c < 4; ++c) {
                     const float df = xa[t][c] + wv4[c];
@@ -556,7 +642,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           __syncwarp();
           if (lane == 0) mbar_arrive(&b_empty[bs]);
 #pragma unroll
-          for (int t = 0; t < TC_TILES; ++t) {
+          for (int t = 0; t < TILES; ++t) {
             float kv[4];
             kernel_profile_n<4>(acc[t], kv, lay.kernel);
 #pragma unroll
@@ -568,12 +654,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           }
         }
         if (warp == 0) TC_TRACE(1, it, 3);
-        mbar_wait_hybrid_backoff(&a_empty[as], ph ^ 1, lane);
+        mbar_wait_hybrid_backoff(&a_empty[as], aph ^ 1, lane);
         tc_fence_after();
         if (warp == 0) TC_TRACE(1, it, 4);
 #pragma unroll
-        for (int t = 0; t < TC_TILES; ++t) {
-          const uint32_t col = TP_COL_A + (as * TC_TILES + t) * 32 + h * 4;
+        for (int t = 0; t < TILES; ++t) {
+          const uint32_t col = M::A + (as * TILES + t) * 32 + h * 4;
           tc_st4(lane_addr + col, s1[t]);
           tc_st4(lane_addr + col + 16, s2[t]);
         }
@@ -586,45 +672,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       }
     }
   } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_NEPI) {
-    // ================= epilogue (D single-buffered: drain both tiles, release, then reduce) =================
+    // ================= epilogue (D single-buffered) =================
     const int q = warp & 3;
     const int etid = tid - TC_EPI_WARP0 * 32;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-    LsRegState<TC_NEPI> ls;
-    ls.init();
-    for (int pass = t0; pass < t1; ++pass) {
-      const uint32_t pl = (uint32_t)(pass - t0);
-      mbar_wait_hybrid_backoff<500>(d_full, pl & 1, lane);
-      tc_fence_after();
-      const int r = q * 32 + lane;
+    const int r = q * 32 + lane;
+    if constexpr (NCH == 1) {
+      // drain both tiles, release the accumulators, then reduce (level set: register-resident state)
+      LsRegState<TC_NEPI> ls;
+      ls.init();
+      for (int pass = t0; pass < t1; ++pass) {
+        const uint32_t pl = (uint32_t)(pass - t0);
+        mbar_wait_hybrid_backoff<500>(d_full, pl & 1, lane);
+        tc_fence_after();
 #pragma unroll 1
-      for (int t = 0; t < TC_TILES; ++t) {
+        for (int t = 0; t < TILES; ++t) {
 #pragma unroll 1
-        for (int c = 0; c < TN / 16; ++c) {
-          uint32_t u[16];
-          tc_ld16(lane_addr + TP_COL_D + t * TN + c * 16, u);
-          tc_wait_ld();
+          for (int c = 0; c < TN / 16; ++c) {
+            uint32_t u[16];
+            tc_ld16(lane_addr + M::D + t * TN + c * 16, u);
+            tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sOut[(t * TN + c * 16 + j) * OUT_LD + r] = __uint_as_float(u[j]);
+            for (int j = 0; j < 16; ++j) sOut[(t * TN + c * 16 + j) * OUT_LD + r] = __uint_as_float(u[j]);
+          }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d_empty);
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty);
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
 #pragma unroll 1
-      for (int t = 0; t < TC_TILES; ++t) {
-        const int tile = pass * TC_TILES + t;
-        if (tile < a.ntiles) {
-          const float* so = sOut + (size_t)t * TN * OUT_LD;
-          if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg<TC_NEPI>(a, so, ls, tile * TM, s0, etid);
-          else epilogue_tile<EPI, TC_NEPI>(a, so, e, tile * TM, s0, etid);
+        for (int t = 0; t < TILES; ++t) {
+          const int tile = pass * TILES + t;
+          if (tile < a.ntiles) {
+            const float* so = sOut + (size_t)t * TN * OUT_LD;
+            if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg<TC_NEPI>(a, so, ls, tile * TM, s0, etid);
+            else epilogue_tile<EPI, TC_NEPI>(a, so, e[0], tile * TM, s0, etid);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
+      }
+      if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg_flush<TC_NEPI>(a, ls, s0, etid);
+      else epilogue_flush<EPI>(a, e[0], s0, etid, TC_NEPI * 32);
+    } else {
+      // one tile, NCH sample chunks: drain and reduce chunk by chunk through one staging tile; the
+      // accumulators are released as soon as the last chunk has left tensor memory (the reduction
+      // state of every chunk lives in shared memory)
+      for (int pass = t0; pass < t1; ++pass) {
+        const uint32_t pl = (uint32_t)(pass - t0);
+        mbar_wait_hybrid_backoff<500>(d_full, pl & 1, lane);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ch = 0; ch < nch; ++ch) {
+#pragma unroll 1
+          for (int c = 0; c < TN / 16; ++c) {
+            uint32_t u[16];
+            tc_ld16(lane_addr + M::D + ch * TN + c * 16, u);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sOut[(c * 16 + j) * OUT_LD + r] = __uint_as_float(u[j]);
+          }
+          if (ch == nch - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d_empty);
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
+          epilogue_tile<EPI, TC_NEPI>(a, sOut, e[ch], pass * TM, s0 + ch * TN, etid);
+          asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
         }
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
+      for (int ch = 0; ch < nch; ++ch) epilogue_flush<EPI>(a, e[ch], s0 + ch * TN, etid, TC_NEPI * 32);
     }
-    if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg_flush<TC_NEPI>(a, ls, s0, etid);
-    else epilogue_flush<EPI>(a, e, s0, etid, TC_NEPI * 32);
   }
 
   tc_fence_before();
@@ -634,19 +752,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   }
 }
 
-template <int EPI, bool PAIRX>
-int tensor_proj_launch_epi(const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
+template <int EPI, bool PAIRX, int NCH>
+int tensor_proj_launch_epi(const KArgs& a, const TpPlan& plan, cudaStream_t st, char* err, size_t errlen) {
   const Layout& l = a.lay;
-  const int gx = tensor_parts(l, a.N, sms), gy = l.Sp / TN;
-  const TpSmem sl = tp_smem_layout(l, EPI, a.k);
-  if (sl.total > TC_SMEM_MAX) {
+  const TpSmem sl = tp_smem_layout(l, EPI, a.k, NCH);
+  if (sl.total > TC_SMEM_MAX || sl.nsb < (uint32_t)TP_NSB_MIN) {
     snprintf(err, errlen, "tensor projection engine: shared memory %u B exceeds 227 KB", sl.total);
     return PSBAX_E_UNSUPPORTED;
   }
   const size_t off_om = l.off_tc + tensor_pack_floats(l);
-  cudaError_t ce = cudaFuncSetAttribute(k_tensor_proj<EPI, PAIRX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
+  cudaError_t ce = cudaFuncSetAttribute(k_tensor_proj<EPI, PAIRX, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sl.total);
   if (ce == cudaSuccess) {
-    k_tensor_proj<EPI, PAIRX><<<dim3(gx, gy), TC_THREADS, sl.total, st>>>(a, off_om);
+    k_tensor_proj<EPI, PAIRX, NCH><<<dim3(plan.gx, plan.gy), TC_THREADS, sl.total, st>>>(a, off_om);
     ce = cudaGetLastError();
   }
   if (ce != cudaSuccess) {
@@ -658,19 +775,23 @@ int tensor_proj_launch_epi(const KArgs& a, int sms, cudaStream_t st, char* err, 
 
 int tensor_proj_launch(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen);  // tensor_proj.cu
 #ifdef PSBAX_TU_PROJ
+template <int EPI>
+int tensor_proj_launch_shape(const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
+  const TpPlan plan = tp_plan(a.lay, a.N, sms, EPI, a.k);
+  if (plan.nch == 4) return tensor_proj_launch_epi<EPI, false, 4>(a, plan, st, err, errlen);
+  if (plan.nch == 2) return tensor_proj_launch_epi<EPI, false, 2>(a, plan, st, err, errlen);
+  // Two row tiles per pass.  Packed-FP32 exact-kernel rows over the row pair: measured per
+  // instantiation (same box, d = 5 / 10 / 32).  The level-set kernel (register-resident epilogue
+  // state, tightest register budget) only gains from d = 13 on (d = 10: 7.78 -> 8.23 ms, d = 32:
+  // 3.01 -> 2.87); top-k and values gain from d = 5 (C5 top-32 8.65 -> 8.48 ms).
+  const bool pairx = a.lay.n > 0 && a.lay.dp4 >= (EPI == EPI_LEVELSET ? 16 : 8);
+  return pairx ? tensor_proj_launch_epi<EPI, true, 1>(a, plan, st, err, errlen)
+               : tensor_proj_launch_epi<EPI, false, 1>(a, plan, st, err, errlen);
+}
 inline int tensor_proj_launch_impl(int epi, const KArgs& a, int sms, cudaStream_t st, char* err, size_t errlen) {
-  // Packed-FP32 exact-kernel rows: measured per instantiation (same box, d = 5 / 10 / 32).  The
-  // level-set kernel (register-resident epilogue state, tightest register budget) only gains from
-  // d = 13 on (d = 10: 7.78 -> 8.23 ms, d = 32: 3.01 -> 2.87); top-k and values gain from d = 5
-  // (C5 top-32 8.65 -> 8.48 ms).
-  const bool pairx = a.lay.n > 0 && a.lay.dp4 >= (epi == EPI_LEVELSET ? 16 : 8);
-#define TP_LAUNCH(E)                                                                      \
-  return pairx ? tensor_proj_launch_epi<E, true>(a, sms, st, err, errlen)                 \
-               : tensor_proj_launch_epi<E, false>(a, sms, st, err, errlen)
-  if (epi == EPI_VALUES) TP_LAUNCH(EPI_VALUES);
-  if (epi == EPI_LEVELSET) TP_LAUNCH(EPI_LEVELSET);
-  TP_LAUNCH(EPI_TOPK);
-#undef TP_LAUNCH
+  if (epi == EPI_VALUES) return tensor_proj_launch_shape<EPI_VALUES>(a, sms, st, err, errlen);
+  if (epi == EPI_LEVELSET) return tensor_proj_launch_shape<EPI_LEVELSET>(a, sms, st, err, errlen);
+  return tensor_proj_launch_shape<EPI_TOPK>(a, sms, st, err, errlen);
 }
 
 #endif

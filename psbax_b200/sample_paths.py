@@ -24,7 +24,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import ENGINE_IDS, KERNEL_IDS, PathsStruct, PsbaxError
+from ._lib import ENGINE_IDS, KERNEL_IDS, MeshStruct, PathsStruct, PsbaxError
 
 F32 = torch.float32
 F64 = torch.float64
@@ -49,6 +49,7 @@ class LevelSetResult:
     maxval: torch.Tensor  # float32 [S]
     argmax: torch.Tensor  # int64 [S] (row_offset + row)
     N: int
+    pooled: Optional[torch.Tensor] = None  # int32 words [ceil(N/32)]: OR of the S masks (computed in the kernel)
 
     def indices(self, s: int) -> torch.Tensor:
         """Row indices of sample ``s``'s super-level set, or ``[argmax]`` when empty."""
@@ -192,22 +193,49 @@ class SamplePathBatch:
                                                  self._stream()), "psbax_eval_sumsq")
         return out
 
-    def levelset(self, X, threshold: float, want_mask: bool = True, row_offset: int = 0) -> LevelSetResult:
-        """Fused evaluation + ``fx > threshold`` for all S paths."""
-        X = self._x(X)
-        N = X.shape[0]
+    def levelset(self, X, threshold: float, want_mask: bool = True, row_offset: int = 0,
+                 want_pooled: bool = False, mesh=None, N: Optional[int] = None) -> LevelSetResult:
+        """Fused evaluation + ``fx > threshold`` for all S paths.
+
+        ``want_pooled``: also return the OR of the S masks (``LevelSetResult.pooled``), formed inside the
+        kernel — the pool ``gen_posterior_sampling_batch`` needs (``posterior_sampling.py:64-78``).
+        ``mesh``: instead of ``X``, a list of d axis tensors; the candidates are rows
+        [row_offset, row_offset + N) of ``reshape_mesh(torch.meshgrid(*axes, indexing='ij'))``
+        (``src/utils.py:264-286``), generated on the device (``N`` defaults to the rest of the mesh)."""
+        ms = None
+        if mesh is not None:
+            if X is not None:
+                raise PsbaxError("pass either X or mesh")
+            if self.input_transform is not None:
+                raise PsbaxError("mesh candidates cannot go through an input transform")
+            axes = [torch.as_tensor(ax).to(self.device, F32).contiguous().reshape(-1) for ax in mesh]
+            if len(axes) != self.d or not 1 <= len(axes) <= 4:
+                raise PsbaxError(f"mesh needs d={self.d} axes (at most 4), got {len(axes)}")
+            total = math.prod(int(ax.numel()) for ax in axes)
+            N = total - row_offset if N is None else int(N)
+            ms = MeshStruct(d=len(axes), reserved=0)
+            for i, ax in enumerate(axes):
+                ms.len[i] = ax.numel()
+                ms.axis[i] = ax.data_ptr()
+            xptr = None
+        else:
+            X = self._x(X)
+            N = X.shape[0]
+            xptr = X.data_ptr()
         with torch.cuda.device(self.device):
             words = (N + 31) // 32
             mask = torch.empty(self.S, words, dtype=torch.int32, device=self.device) if want_mask else None
+            pooled = torch.empty(words, dtype=torch.int32, device=self.device) if want_pooled else None
             count = torch.empty(self.S, dtype=torch.int64, device=self.device)
             maxval = torch.empty(self.S, dtype=F32, device=self.device)
             argmax = torch.empty(self.S, dtype=torch.int64, device=self.device)
             ws = self._workspace(N, 0)
-            _lib.check(self.lib.psbax_eval_levelset(
-                C.byref(self._struct), self._pack.data_ptr(), X.data_ptr(), N, row_offset,
-                float(threshold), _ptr(mask), words, count.data_ptr(), maxval.data_ptr(),
-                argmax.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()), "psbax_eval_levelset")
-        return LevelSetResult(mask, count, maxval, argmax, N)
+            _lib.check(self.lib.psbax_eval_levelset_ex(
+                C.byref(self._struct), self._pack.data_ptr(), xptr, C.byref(ms) if ms is not None else None, N,
+                row_offset, float(threshold), _ptr(mask), words, _ptr(pooled), count.data_ptr(),
+                maxval.data_ptr(), argmax.data_ptr(), ws.data_ptr(), ws.numel(), self._stream()),
+                "psbax_eval_levelset_ex")
+        return LevelSetResult(mask, count, maxval, argmax, N, pooled)
 
     def levelset_streamed(self, X_host: torch.Tensor, threshold: float, chunk_rows: int = 1 << 21,
                           row_offset: int = 0):

@@ -26,9 +26,12 @@ def test_header_symbols_are_exported():
 
 def test_version_and_struct_size():
     lib = _lib.load()
-    assert lib.psbax_version() == 1
+    assert lib.psbax_version() == 2
     # 8 int32 + 6 pointers + 4 floats
     assert C.sizeof(_lib.PathsStruct) == 8 * 4 + 6 * 8 + 4 * 4
+    assert C.sizeof(_lib.MeshStruct) == 2 * 4 + 4 * 8 + 4 * 8
+    # the product build keeps no trace state (include/psbax_b200.h: no global mutable state)
+    assert lib.psbax_debug_trace_buffer(None) == -2
 
 
 def test_invalid_arguments_report_errors():

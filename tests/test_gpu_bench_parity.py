@@ -72,3 +72,40 @@ def test_bench_problem_values_mask_counts(bench_case, engine):
     assert (np.abs(mv - best) <= tol).all()
     assert (np.abs(ref[am, np.arange(S)] - best) <= 2 * tol).all()
     print(f"{engine}: max value error {float((worst / tol).max()):.3f} x strict tolerance")
+
+
+@pytest.mark.parametrize("engine", ["auto", "tensor", "simt"])
+def test_mesh_rows_and_pooled_mask(bench_case, engine):
+    """psbax_eval_levelset_ex: rows generated on the device from the mesh axes are the rows of
+    reshape_mesh(get_mesh(2, steps)) bit for bit (same masks / counts / arg max as the uploaded X*),
+    and the pooled word is the OR of the S mask words (posterior_sampling.py:64-78)."""
+    p, X, ref, tau = bench_case
+    N = X.shape[0]
+    batch = to_batch(p, engine=engine)
+    ax = torch.linspace(0, 1, STEPS, dtype=torch.float64).float()  # the float32 cast of the oracle's float64 mesh axes
+    full = batch.levelset(X.cuda(), tau, want_mask=True, want_pooled=True)
+    words = full.mask.cpu().numpy().astype(np.uint32)
+    assert (np.bitwise_or.reduce(words, axis=0) == full.pooled.cpu().numpy().astype(np.uint32)).all()
+    # a shard of the mesh that starts and ends inside a mesh row and inside a mask word
+    lo, n = 3 * STEPS + 517, 300_001
+    shard = batch.levelset(X[lo:lo + n].cuda(), tau, want_mask=True, want_pooled=True, row_offset=lo)
+    mesh = batch.levelset(None, tau, want_mask=True, want_pooled=True, row_offset=lo, mesh=[ax, ax], N=n)
+    assert torch.equal(mesh.mask, shard.mask) and torch.equal(mesh.pooled, shard.pooled)
+    assert torch.equal(mesh.count, shard.count) and torch.equal(mesh.argmax, shard.argmax)
+    assert torch.equal(mesh.maxval, shard.maxval)
+    # pooled only: nothing but N / 8 bytes + the per-sample scalars leaves the kernel
+    only = batch.levelset(None, tau, want_mask=False, want_pooled=True, mesh=[ax, ax])
+    assert only.mask is None and torch.equal(only.pooled, full.pooled) and torch.equal(only.count, full.count)
+
+
+def test_mesh_3d_matches_uploaded_rows():
+    from helpers import random_params
+
+    p = random_params(20, 96, 3, 17, kernel="matern32", seed=5)
+    axes = [torch.linspace(0, 1, 7), torch.linspace(0.1, 0.9, 13), torch.rand(11)]
+    X = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).reshape(-1, 3).float()
+    for engine in ("auto", "simt"):
+        batch = to_batch(p, engine=engine)
+        a = batch.levelset(X.cuda(), -0.5, want_pooled=True)
+        b = batch.levelset(None, -0.5, want_pooled=True, mesh=axes)
+        assert torch.equal(a.mask, b.mask) and torch.equal(a.pooled, b.pooled) and torch.equal(a.argmax, b.argmax)
