@@ -134,6 +134,9 @@ Layout make_layout(const psbax_paths_t* p) {
   return l;
 }
 
+// fused top-k: [Sp] seed thresholds + [TOPK_SEED_ROWS][Sp] pre-pass values (see psbax_eval_topk)
+size_t topk_seed_bytes(const Layout& l) { return ((size_t)l.Sp + (size_t)TOPK_SEED_ROWS * l.Sp) * sizeof(float) + 256; }
+
 // persistent grid: gx CTAs over the row tiles, gy sample chunks
 void grid_for(const Layout& l, long long N, int sms, int* gx, int* gy, int* ntiles) {
   const long long nt = (N + TM - 1) / TM;
@@ -254,7 +257,8 @@ int psbax_workspace_bytes(const psbax_paths_t* paths, int64_t N, int32_t k, size
   if (is_tensor_mode(l.mode)) gx = l.tc_proj ? sms : tensor_parts(l, N, sms);  // (upper bound for the projection variant's plans)
   const size_t per = (size_t)gx * l.Sp;
   const size_t ls = per * (sizeof(unsigned int) + sizeof(float) + sizeof(int));
-  const size_t tk = per * (size_t)(k > 0 ? k : 1) * (sizeof(float) + sizeof(int));
+  size_t tk = per * (size_t)(k > 0 ? k : 1) * (sizeof(float) + sizeof(int));
+  if (k > 0) tk += topk_seed_bytes(l);  // seed thresholds + the values of the pre-pass rows
   *bytes = (ls > tk ? ls : tk) + 256;
   return PSBAX_OK;
 }
@@ -399,6 +403,30 @@ int psbax_eval_topk(const psbax_paths_t* paths, const void* pack, const float* X
   a.p_tv = static_cast<float*>(workspace);
   a.p_ti = reinterpret_cast<int*>(a.p_tv + per);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // Seed thresholds.  Every CTA starts with empty lists, so its first tiles send nearly every row
+  // through the list merge — with few tiles per CTA (C3: 149,361 rows = 8 tiles per SM) that cold
+  // start cost more than the contraction itself.  A pre-pass evaluates the first 2048 rows (values
+  // kernel, same arithmetic) and takes each sample's k-th largest value there: a lower bound of the
+  // k-th largest over all N rows, so the main launch only ever merges ~N k / 2048 rows per sample.
+  {
+    const long long tiles_per_cta = (N + TM - 1) / TM / (parts > 0 ? parts : 1);
+    if (N >= 8LL * TOPK_SEED_ROWS && tiles_per_cta < 128 && k <= TOPK_SEED_ROWS / 8) {
+      float* seed = reinterpret_cast<float*>(reinterpret_cast<char*>(a.p_ti + per) + 128);
+      seed = reinterpret_cast<float*>(((uintptr_t)seed + 127) & ~(uintptr_t)127);
+      float* svals = seed + l.Sp;
+      Prepared pv;
+      rc = prepare(paths, pack, X, TOPK_SEED_ROWS, &pv);
+      if (rc) return rc;
+      pv.a.out = svals;
+      pv.a.ld_out = l.Sp;
+      if (is_tensor_mode(l.mode)) rc = tensor_launch_any(EPI_VALUES, pv.a, pv.sms, st, g_err, sizeof(g_err));
+      else rc = simt_launch(EPI_VALUES, pv.a, pv.grid, st, g_err, sizeof(g_err));
+      if (rc) return rc;
+      k_topk_seed<<<l.S, 256, 0, st>>>(svals, TOPK_SEED_ROWS, l.Sp, k, seed);
+      CUDA_TRY(cudaGetLastError());
+      a.thr_seed = seed;
+    }
+  }
   if (is_tensor_mode(l.mode)) rc = tensor_launch_any(EPI_TOPK, a, pr.sms, st, g_err, sizeof(g_err));
   else rc = simt_launch(EPI_TOPK, a, pr.grid, st, g_err, sizeof(g_err));
   if (rc) return rc;

@@ -100,6 +100,7 @@ struct KArgs {
   int k;
   float* p_tv;
   int* p_ti;
+  const float* thr_seed;  // TOPK, optional [Sp]: admission threshold known before the launch (see psbax_eval_topk)
   long long* trace;  // optional device buffer for clock64 traces (psbax_debug_trace_buffer)
   // LEVELSET, optional: pooled[w] |= OR over the S samples of the mask words (bit i = row i is in at
   // least one path's super-level set); zeroed by the caller, combined with atomic ORs

@@ -100,6 +100,42 @@ __global__ void __launch_bounds__(128) k_topk_merge(const float* __restrict__ in
   }
 }
 
+// Seed thresholds of the fused top-k: thr[s] = a value <= the k-th largest of vals[0..M)[s]
+// (the k-th largest DISTINCT value, minus a relative margin of 2^-20), or -inf when there are fewer
+// than k distinct values.  One block of 256 threads per sample, M <= 2048: k rounds of block max.
+constexpr int TOPK_SEED_ROWS = 2048;
+__global__ void __launch_bounds__(256) k_topk_seed(const float* __restrict__ vals, int M, long long ld, int k,
+                                                   float* __restrict__ thr) {
+  __shared__ float sw[8];
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float v[TOPK_SEED_ROWS / 256];
+#pragma unroll
+  for (int j = 0; j < TOPK_SEED_ROWS / 256; ++j) {
+    const int idx = tid + j * 256;
+    v[j] = idx < M ? vals[(long long)idx * ld + s] : -CUDART_INF_F;
+  }
+  float kth = -CUDART_INF_F;
+  for (int round = 0; round < k; ++round) {
+    float m = v[0];
+#pragma unroll
+    for (int j = 1; j < TOPK_SEED_ROWS / 256; ++j) m = fmaxf(m, v[j]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if (lane == 0) sw[warp] = m;
+    __syncthreads();
+    m = sw[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sw[w]);
+    __syncthreads();
+    kth = m;
+    if (m == -CUDART_INF_F) break;
+#pragma unroll
+    for (int j = 0; j < TOPK_SEED_ROWS / 256; ++j)
+      if (v[j] == m) v[j] = -CUDART_INF_F;  // every copy goes: the k-th distinct value is still a lower bound
+  }
+  if (tid == 0) thr[s] = (kth == -CUDART_INF_F) ? kth : kth - fabsf(kth) * 9.5367431640625e-7f - 1e-37f;
+}
+
 // ---------------------------------------------------------------------------------
 // pack kernel
 // ---------------------------------------------------------------------------------

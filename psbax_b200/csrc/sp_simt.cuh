@@ -62,25 +62,49 @@ __device__ __forceinline__ void epi_init(const EpiSmem& e, int epi, int k, int t
   }
 }
 
-// Insert (v, idx) into the sorted (best first) k-list of one sample.  Called by a
-// full warp with warp-uniform (v, idx).
-__device__ __forceinline__ void topk_insert_warp(float* tv, int* ti, int k, float v, int idx,
-                                                 int lane) {
+// Merge the candidates of one 32-row group into the sorted (best first) k-list of one sample.
+// Called by a full warp; lane j of the group holds candidate (y, row) when bit j of `m` is set.
+//
+// Rank-based: the list entries (lane-distributed: lane j owns entries j and j + 32) and the
+// candidates are merged in ONE pass over the candidates — each iteration broadcasts one candidate
+// and every lane updates the new rank of its own list entries and of its own candidate; the
+// iterations are independent (no store -> load round trip per candidate), and every element then
+// writes itself to its new position (measured on the C3 shape: a cold list cost ~340 cycles per
+// serial insertion, ~150 per candidate this way; what removes the cold start itself is the seed
+// threshold, see psbax_eval_topk).
+// The order is the total order of better(): larger value first, ties to the smaller index.
+__device__ __forceinline__ void topk_merge_group(float* tv, int* ti, int k, float y, int row,
+                                                 unsigned int m, int lane) {
   const int q0 = lane, q1 = lane + 32;
-  float e0v = -CUDART_INF_F, e1v = -CUDART_INF_F, p0v = 0.f, p1v = 0.f;
-  int e0i = 0x7fffffff, e1i = 0x7fffffff, p0i = 0, p1i = 0;
+  const bool two = k > 32;  // warp-uniform
+  float e0v = -CUDART_INF_F, e1v = -CUDART_INF_F;
+  int e0i = 0x7fffffff, e1i = 0x7fffffff;
   if (q0 < k) { e0v = tv[q0]; e0i = ti[q0]; }
-  if (q1 < k) { e1v = tv[q1]; e1i = ti[q1]; }
-  if (q0 > 0 && q0 < k) { p0v = tv[q0 - 1]; p0i = ti[q0 - 1]; }
-  if (q1 < k) { p1v = tv[q1 - 1]; p1i = ti[q1 - 1]; }
-  const bool a0 = (q0 < k) && better(e0v, e0i, v, idx);
-  const bool a1 = (q1 < k) && better(e1v, e1i, v, idx);
-  const int p = __popc(__ballot_sync(0xffffffffu, a0)) + __popc(__ballot_sync(0xffffffffu, a1));
-  __syncwarp();
-  if (p < k) {
-    if (q0 < k && q0 >= p) { tv[q0] = (q0 == p) ? v : p0v; ti[q0] = (q0 == p) ? idx : p0i; }
-    if (q1 < k && q1 >= p) { tv[q1] = (q1 == p) ? v : p1v; ti[q1] = (q1 == p) ? idx : p1i; }
+  if (two && q1 < k) { e1v = tv[q1]; e1i = ti[q1]; }
+  const bool mine = (m >> lane) & 1u;
+  int r0 = q0, r1 = q1;  // new ranks of this lane's list entries
+  int rc = 0;            // new rank of this lane's candidate
+  unsigned int mm = m;
+  while (mm) {
+    const int src = __ffs(mm) - 1;
+    mm &= mm - 1;
+    const float cv = __shfl_sync(0xffffffffu, y, src);
+    const int ci = __shfl_sync(0xffffffffu, row, src);
+    const bool b0 = better(e0v, e0i, cv, ci);  // (unused slots hold (-inf, int max): never better)
+    int nb = __popc(__ballot_sync(0xffffffffu, b0));
+    if (!b0) ++r0;  // the candidate goes in front of this entry
+    if (two) {
+      const bool b1 = better(e1v, e1i, cv, ci);
+      nb += __popc(__ballot_sync(0xffffffffu, b1));
+      if (!b1) ++r1;
+    }
+    if (mine && better(cv, ci, y, row)) ++rc;  // candidates in front of mine
+    if (lane == src) rc += nb;                 // + list entries in front of mine
   }
+  __syncwarp();  // every lane holds its old entries in registers: positions may now be overwritten
+  if (q0 < k && r0 < k && r0 != q0) { tv[r0] = e0v; ti[r0] = e0i; }
+  if (two && q1 < k && r1 < k && r1 != q1) { tv[r1] = e1v; ti[r1] = e1i; }
+  if (mine && rc < k) { tv[rc] = y; ti[rc] = row; }
   __syncwarp();
 }
 
@@ -161,7 +185,10 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const float* sOut,
       // The list's last entry is the admission threshold: its value stays in a register and is
       // re-read after insertions.  The pre-filter is y >= threshold; ties on the value are sorted out
       // by the insertion itself (an entry that is not better than the k-th one is not inserted).
-      float thv = tv[k - 1];
+      // a.thr_seed (optional): a lower bound of the sample's k-th largest value over the whole launch
+      // (from a pre-pass over the first rows); rows below it can never enter the final list
+      const float seedv = a.thr_seed != nullptr ? __ldg(a.thr_seed + s) : -CUDART_INF_F;
+      float thv = fmaxf(tv[k - 1], seedv);
       const bool full = (long long)row0 + TM <= N;
 #pragma unroll
       for (int g = 0; g < TM / 32; ++g) {
@@ -170,14 +197,8 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const float* sOut,
         const float y = fmaf(sOut[sl * OUT_LD + r], a.ystd, a.c0);
         unsigned int m = __ballot_sync(0xffffffffu, (full || row < N) && y >= thv);
         if (m) {
-          do {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const float cv = __shfl_sync(0xffffffffu, y, src);
-            const int ci = __shfl_sync(0xffffffffu, (int)row, src);
-            topk_insert_warp(tv, ti, k, cv, ci, lane);
-          } while (m);
-          thv = tv[k - 1];
+          topk_merge_group(tv, ti, k, y, (int)row, m, lane);
+          thv = fmaxf(tv[k - 1], seedv);
         }
       }
     }

@@ -253,24 +253,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   const int npass = (a.ntiles + TILES - 1) / TILES;
   int t0, t1;
   tc_tile_range(npass, gridDim.x, blockIdx.x, &t0, &t1);
-  EpiSmem e[NCH];
-#pragma unroll
-  for (int c = 0; c < NCH; ++c) e[c] = epi_carve(reinterpret_cast<float*>(smem + sl.state + c * sl.state_stride), EPI, a.k);
+  // reduction state of sample chunk c (carved on the fly: an array of these would live in local memory)
+  auto epi_of = [&](int c) { return epi_carve(reinterpret_cast<float*>(smem + sl.state + c * sl.state_stride), EPI, a.k); };
 
   for (int i = tid; i < round_up(dp4, 4); i += TC_THREADS) sIl[i] = __ldg(a.pack + lay.off_invls + i);
   // x tile of the exact-kernel rows: [i][row] (tile 0, tile 1) pairs for the packed-FP32 path, else
   // [tile][i][row] for the scalar path.  A template parameter, not a runtime branch: at the
   // 80-register cap the mere presence of the second path cost the cos path 10 % (spills).
   constexpr bool pairx = PAIRX;
-  if (lay.n > 0)  // padding dimensions d..dp4-1 are read (times inv_ls = 0) but never refilled
-    for (int i = tid; i < TILES * (dp4 - d) * TM; i += TC_THREADS) {
-      if (pairx) {
-        sX[d * TM * TILES + i] = 0.f;
-      } else {
-        const int t = i / ((dp4 - d) * TM), r = i % ((dp4 - d) * TM);
-        sX[(t * dp4 + d) * TM + r] = 0.f;
+  if (lay.n > 0) {  // padding dimensions d..dp4-1 are read but never refilled
+    if (TILES == 1) {  // [dim pair][row][2]
+      for (int i = tid; i < dp4 * TM; i += TC_THREADS) sX[i] = 0.f;
+    } else {
+      for (int i = tid; i < TILES * (dp4 - d) * TM; i += TC_THREADS) {
+        if (pairx) {
+          sX[d * TM * TILES + i] = 0.f;
+        } else {
+          const int t = i / ((dp4 - d) * TM), r = i % ((dp4 - d) * TM);
+          sX[(t * dp4 + d) * TM + r] = 0.f;
+        }
       }
     }
+  }
   const bool bias_in_x = tp_bias_in_x(d);
   float* sBias = reinterpret_cast<float*>(smem + sl.bias);
   if (!bias_in_x)
@@ -292,8 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_NEPI) {
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) epi_init(e[c], EPI, a.k, tid - TC_EPI_WARP0 * 32, TC_NEPI * 32);
+    for (int c = 0; c < NCH; ++c) epi_init(epi_of(c), EPI, a.k, tid - TC_EPI_WARP0 * 32, TC_NEPI * 32);
   }
   tc_fence_before();
   __syncthreads();
@@ -479,6 +482,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           const int rr = idx / d, i = idx - rr * d;
           const float xv = (base + idx < lim) ? __ldg(a.X + base + idx) : 0.f;
           if (pairx) sX[(i * TM + (rr & 127)) * TILES + (rr >> 7)] = xv;  // one LDS.64 feeds a packed FFMA2
+          else if (TILES == 1) sX[((i >> 1) * TM + rr) * 2 + (i & 1)] = xv * sIl[i];  // scaled, [dim pair][row][2]
           else sX[((rr >> 7) * dp4 + i) * TM + (rr & 127)] = xv;
         }
         asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
@@ -588,31 +592,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
 #pragma unroll
             for (int j = 0; j < 4; ++j) unpack2(acc2[j], acc[0][j], acc[TILES - 1][j]);
           } else if constexpr (TILES == 1) {
-            // one row per thread: packed FP32 over PAIRS OF FEATURES.  df = (x * inv_ls) + (-x_t * inv_ls)
-            // for features (2p, 2p + 1) at once; the scaled coordinate is broadcast into both halves.
-            const float* xs = sX + q * 32 + lane;
-            uint64_t acc2[2] = {0ull, 0ull};
+            // one row per thread: packed FP32 over PAIRS OF DIMENSIONS.  The scaled row sits in shared
+            // memory as (x_i, x_i+1) / ls pairs, a table row is read as 16-byte pieces = two pairs:
+            //   df = (x_i, x_i+1) / ls + (-x_t)[i, i+1] / ls,  (acc_even, acc_odd) += df * df,  r^2 = acc_even + acc_odd
+            const uint64_t* xs2 = reinterpret_cast<const uint64_t*>(sX) + q * 32 + lane;
+            uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
+            const uint64_t one2 = pack2(1.0f, 1.0f);
+#pragma unroll 2
             for (int i0 = 0; i0 < dp4; i0 += 4) {
-              uint64_t xb[4];
+              const uint64_t xa = xs2[(i0 >> 1) * TM], xb = xs2[((i0 >> 1) + 1) * TM];
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float xv = xs[(i0 + c) * TM] * sIl[i0 + c];
-                xb[c] = pack2(xv, xv);
-              }
-#pragma unroll
-              for (int pj = 0; pj < 2; ++pj) {
-                const float4 wa = *reinterpret_cast<const float4*>(ft + (2 * pj) * OS + i0);
-                const float4 wb = *reinterpret_cast<const float4*>(ft + (2 * pj + 1) * OS + i0);
-                const float wa4[4] = {wa.x, wa.y, wa.z, wa.w}, wb4[4] = {wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  const uint64_t df = ffma2(xb[c], pack2(1.0f, 1.0f), pack2(wa4[c], wb4[c]));
-                  acc2[pj] = ffma2(df, df, acc2[pj]);
-                }
+              for (int j = 0; j < 4; ++j) {
+                const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(ft + j * OS + i0);
+                const uint64_t dfa = ffma2(xa, one2, w.x), dfb = ffma2(xb, one2, w.y);
+                acc2[j] = ffma2(dfa, dfa, acc2[j]);
+                acc2[j] = ffma2(dfb, dfb, acc2[j]);
               }
             }
-            unpack2(acc2[0], acc[0][0], acc[0][1]);
-            unpack2(acc2[1], acc[0][2], acc[0][3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float ev, od;
+              unpack2(acc2[j], ev, od);
+              acc[0][j] = ev + od;
+            }
           } else {
             const float* xs = sX + q * 32 + lane;
 #pragma unroll
@@ -668,6 +670,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[as]);
         if (warp == 0) TC_TRACE(1, it, 5);
+        if (lane == 0 && (warp == 5 || warp == 10 || warp == 15)) TC_TRACE(3, it, 1 + warp / 5);  // other producers: stored
         if (++bs == NSB) { bs = 0; bph ^= 1; }
       }
     }
@@ -706,21 +709,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           if (tile < a.ntiles) {
             const float* so = sOut + (size_t)t * TN * OUT_LD;
             if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg<TC_NEPI>(a, so, ls, tile * TM, s0, etid);
-            else epilogue_tile<EPI, TC_NEPI>(a, so, e[0], tile * TM, s0, etid);
+            else epilogue_tile<EPI, TC_NEPI>(a, so, epi_of(0), tile * TM, s0, etid);
           }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
       }
       if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg_flush<TC_NEPI>(a, ls, s0, etid);
-      else epilogue_flush<EPI>(a, e[0], s0, etid, TC_NEPI * 32);
+      else epilogue_flush<EPI>(a, epi_of(0), s0, etid, TC_NEPI * 32);
     } else {
       // one tile, NCH sample chunks: drain and reduce chunk by chunk through one staging tile; the
       // accumulators are released as soon as the last chunk has left tensor memory (the reduction
       // state of every chunk lives in shared memory)
       for (int pass = t0; pass < t1; ++pass) {
         const uint32_t pl = (uint32_t)(pass - t0);
+        if (etid == 0) TC_TRACE(2, pl, 0);
         mbar_wait_hybrid_backoff<500>(d_full, pl & 1, lane);
         tc_fence_after();
+        if (etid == 0) TC_TRACE(2, pl, 1);
 #pragma unroll 1
         for (int ch = 0; ch < nch; ++ch) {
 #pragma unroll 1
@@ -735,13 +740,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(d_empty);
+            if (etid == 0) TC_TRACE(2, pl, 2);
           }
           asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
-          epilogue_tile<EPI, TC_NEPI>(a, sOut, e[ch], pass * TM, s0 + ch * TN, etid);
+          epilogue_tile<EPI, TC_NEPI>(a, sOut, epi_of(ch), pass * TM, s0 + ch * TN, etid);
           asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
         }
+        if (etid == 0) TC_TRACE(2, pl, 3);
       }
-      for (int ch = 0; ch < nch; ++ch) epilogue_flush<EPI>(a, e[ch], s0 + ch * TN, etid, TC_NEPI * 32);
+      for (int ch = 0; ch < nch; ++ch) epilogue_flush<EPI>(a, epi_of(ch), s0 + ch * TN, etid, TC_NEPI * 32);
     }
   }
 
