@@ -351,6 +351,40 @@ def eval_paths(p: PathParams, X: torch.Tensor, chunk: int = 8192) -> torch.Tenso
     return out
 
 
+def eval_paths_best_effort(p: PathParams, X: torch.Tensor, block: int = 65536) -> torch.Tensor:
+    """The "best-effort CPU" form of the same path: float32, shared
+    basis, all S paths at once, one blocked GEMM pair per ``block`` rows on all host threads —
+    what a careful CPU implementation would do, so that the GPU / CPU ratio is not just the
+    reference's Python overhead.  ``p`` must be a shared-basis (G == 1) parameter set.  [N, S] float32."""
+    assert p.G == 1, "best-effort CPU line is the shared-basis form"
+    f32 = torch.float32
+    X = X.to(f32)
+    om = p.omega[0].to(f32).T.contiguous() if p.L > 0 else None  # [d, L]
+    b = p.bias[0].to(f32) if p.L > 0 else None
+    Wt = p.W.to(f32).T.contiguous() if p.L > 0 else None          # [L, S]
+    Xt = p.Xtrain.to(f32) if p.n > 0 else None
+    Vt = p.V.to(f32).T.contiguous() if p.n > 0 else None          # [n, S]
+    il = p.inv_ls.to(f32) if p.n > 0 else None
+    xt2 = (Xt * Xt).sum(-1) if p.n > 0 else None
+    out = torch.empty(X.shape[0], p.S, dtype=f32)
+    for a in range(0, X.shape[0], block):
+        Xc = X[a:a + block]
+        f = torch.zeros(Xc.shape[0], p.S, dtype=f32)
+        if p.L > 0:
+            Phi = torch.addmm(b, Xc, om)
+            Phi.cos_()
+            f = Phi @ Wt
+        if p.n > 0:
+            Z = Xc * il
+            if p.kernel == "linear":
+                f = f + (Z @ Xt.T) @ Vt
+            else:  # GEMM form of the squared distances (what a BLAS-bound CPU code would use)
+                r2 = ((Z * Z).sum(-1, keepdim=True) + xt2[None, :] - 2.0 * (Z @ Xt.T)).clamp_min_(0.0)
+                f = f + kernel_profile(r2, p.kernel) @ Vt
+        out[a:a + block] = p.y_mean + p.y_std * (p.mean_const + f)
+    return out
+
+
 def eval_path_grad(p: PathParams, X: torch.Tensor, s: int) -> torch.Tensor:
     """d f_s / d x at X [N, d] -> [N, d] (what ``LBFGSB`` obtains by autograd,
     ``src/algorithms/lbfgsb.py:29-39``)."""
