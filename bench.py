@@ -3,14 +3,20 @@
 GP sample-path evals/sec = candidates x samples / time(evaluate + reduce)).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2|c3|c4|c5] [--engine auto|simt|tensor|tensor_bf16]
 
-Workload (BASELINE.json configs[1]): level-set estimation on a dense 2-D grid,
-4096 x 4096 = 16,777,216 candidates per GPU, S = 64 Matheron sample paths, L = 1000 RFF
-features, n = 64 training points (standardized Himmelblau), Matern-5/2 ARD,
-threshold = 55th percentile.  One "step" = one pass of the fused evaluate + level-set
-reduction over the rank's candidate shard (weak scaling: every GPU holds its own 4096 x 4096
-slab of a (gpus*4096) x 4096 grid; no data-path collective for the level set).
-Inputs are larger than L2 (134 MB of X* + 134 MB of mask per pass), so no L2 flush is needed.
+Default workload c2 (BASELINE.json configs[1], the one the metric is quoted on): level-set
+estimation on a dense 2-D grid, 4096 x 4096 = 16,777,216 candidates per GPU, S = 64 Matheron
+sample paths, L = 1000 RFF features, n = 64 training points (standardized Himmelblau), Matern-5/2
+ARD, threshold = 55th percentile.  One "step" = one pass of the fused evaluate + reduce kernel over
+the rank's candidate shard.  The other BASELINE configs (c3 GB1 top-k, c4 DiscoBAX subset-select,
+c5 Ackley ES scoring) are selected with --workload; each prints the same JSON line with the
+roofline of ITS binding pipe (max over tensor, MUFU, FFMA and HBM).
+
+Under torchrun (N > 1) the c2 line also carries two extra legs:
+`topk_collective` (c3 shape sharded by rows, fused local top-k + ONE NCCL all-gather + merge on one
+stream, asserted bit-identical to the unsharded launch) and `strong` (a 3163 x 3163 = 1.0e7-row
+level set split over the N GPUs).
 
 Printed JSON keys follow the driver contract; see DESIGN.md section "Measurement".
 """
@@ -31,16 +37,29 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 GRID = 4096
-S, L, NTRAIN, D = 64, 1000, 64, 2
+S, L, NTRAIN, D = 64, 1000, 64, 2  # c2 (tests/test_gpu_bench_parity.py reads these)
 KERNEL = "matern52"
 NOISE = 1e-4
 TAU_Q = 0.55
 METRIC = "gp_sample_path_evals_per_sec"
 UNIT = "candidate*sample evals/s"
+L2_BYTES = 126 << 20
+STRONG_STEPS = 3163  # 3163^2 = 10,004,569 rows: the N = 1e7 grid of SURVEY.md section 8d
+
+WORKLOADS = {
+    "c2": dict(name="level-set on a dense 2-D grid (BASELINE configs[1])", op="levelset", N=GRID * GRID, d=2, S=64,
+               L=1000, n=64, kernel=KERNEL, noise=NOISE),
+    "c3": dict(name="GB1 protein fitness top-k, synthetic 32-d embeddings (BASELINE configs[2])", op="topk", k=10,
+               N=149_361, d=32, S=256, L=1000, n=512, kernel=KERNEL, noise=1e-2),
+    "c4": dict(name="DiscoBAX gene-intervention set selection, synthetic features (BASELINE configs[3])",
+               op="subset", k=10, B=100, N=17_176, d=5, S=1024, L=1000, n=128, kernel=KERNEL, noise=1e-2),
+    "c5": dict(name="local BO Ackley-10D: ES populations scored on S sample paths (BASELINE configs[4])",
+               op="argmax", N=10_000_000, d=10, S=32, L=1000, n=122, kernel=KERNEL, noise=1e-3),
+}
 
 
 # ------------------------------------------------------------------------------------------
-# synthetic config-2 problem (same on every rank: seed 0 for the model, grid is analytic)
+# synthetic problems (same on every rank: seed 0 for the model; candidates seed 1234)
 # ------------------------------------------------------------------------------------------
 def himmelblau(X):
     Z = 12.0 * X - 6.0
@@ -48,7 +67,16 @@ def himmelblau(X):
     return -((a ** 2 + b - 11) ** 2 + (a + b ** 2 - 7) ** 2)
 
 
+def ackley(X):
+    Z = 65.536 * X - 32.768
+    d = Z.shape[1]
+    return -(-20.0 * torch.exp(-0.2 * torch.sqrt((Z ** 2).sum(-1) / d))
+             - torch.exp(torch.cos(2 * math.pi * Z).sum(-1) / d) + 20.0 + math.e)
+
+
 def problem():
+    """The c2 model: n = 64 training points U[0,1]^2, y = Himmelblau, ARD lengthscales U[0.1, 0.5],
+    tau = 55th percentile of f over 10,000 random points (demos/level-set.py:42-57)."""
     gen = torch.Generator().manual_seed(0)
     Xt = torch.rand(NTRAIN, D, dtype=torch.float64, generator=gen)
     y = himmelblau(Xt)
@@ -59,13 +87,72 @@ def problem():
     return Xt, y, ls, tau
 
 
+def problem_for(wl):
+    """(train_X, train_Y, lengthscale, tau) of a workload ("Synthetic inputs per
+    config"): V then comes from the actual Matheron solve on these data."""
+    w = WORKLOADS[wl]
+    if wl == "c2":
+        return problem()
+    gen = torch.Generator().manual_seed(0)
+    n, d = w["n"], w["d"]
+    if wl == "c3":  # 32-d N(0,1) embeddings; fitness = smooth function of a few projections
+        Xt = torch.randn(n, d, dtype=torch.float64, generator=gen)
+        P = torch.randn(d, 3, dtype=torch.float64, generator=gen) / math.sqrt(d)
+        y = torch.sin(Xt @ P[:, 0]) + 0.5 * torch.cos(2.0 * (Xt @ P[:, 1])) + 0.3 * (Xt @ P[:, 2])
+        ls = 4.0 + 2.0 * torch.rand(d, dtype=torch.float64, generator=gen)
+    elif wl == "c4":  # min-max normalised PCA features (discobax_runner.py:78)
+        Xt = torch.rand(n, d, dtype=torch.float64, generator=gen)
+        y = torch.sin(3.0 * Xt.sum(-1)) + 0.5 * torch.cos(5.0 * Xt[:, 0])
+        ls = 0.2 + 0.4 * torch.rand(d, dtype=torch.float64, generator=gen)
+    else:  # c5: 22 initial + 100 acquired points of negated Ackley on [0,1]^10
+        Xt = torch.rand(n, d, dtype=torch.float64, generator=gen)
+        y = ackley(Xt)
+        ls = 0.3 + 0.5 * torch.rand(d, dtype=torch.float64, generator=gen)
+    return Xt, y, ls, None
+
+
+def candidates_for(wl, rank, world, device, rows=None):
+    """This rank's candidate rows, float32 on `device`."""
+    w = WORKLOADS[wl]
+    if wl == "c2":
+        return grid_slab(rank, world, device)
+    g = torch.Generator().manual_seed(1234 + 7919 * rank)
+    N = rows or w["N"]
+    if wl == "c3":
+        return torch.randn(N, w["d"], dtype=torch.float32, generator=g).to(device)
+    return torch.rand(N, w["d"], dtype=torch.float32, generator=g).to(device)
+
+
 def grid_slab(rank, world, device):
     """Rows [rank*GRID^2, (rank+1)*GRID^2) of reshape_mesh(get_mesh(2, .)) for a
     (world*GRID) x GRID grid ('ij' order: first coordinate slowest), float32 on `device`."""
-    a0 = torch.linspace(0, 1, world * GRID, dtype=torch.float64)[rank * GRID:(rank + 1) * GRID]
-    a1 = torch.linspace(0, 1, GRID, dtype=torch.float64)
-    X = torch.stack(torch.meshgrid(a0, a1, indexing="ij"), dim=-1).reshape(-1, 2)
-    return X.to(torch.float32).to(device)
+    a0, a1 = grid_axes(world)
+    X = torch.stack(torch.meshgrid(a0[rank * GRID:(rank + 1) * GRID], a1, indexing="ij"), dim=-1).reshape(-1, 2)
+    return X.to(device)
+
+
+def grid_axes(world):
+    """float32 mesh axes of the (world*GRID) x GRID grid (linspace in float64, as the reference's
+    get_mesh, then the float32 cast the GPU path computes in)."""
+    return (torch.linspace(0, 1, world * GRID, dtype=torch.float64).to(torch.float32),
+            torch.linspace(0, 1, GRID, dtype=torch.float64).to(torch.float32))
+
+
+def workload_config(wl, gpus):
+    """Names the workload; the SAME key set and values for both arms (ours / reference)."""
+    w = WORKLOADS[wl]
+    cfg = {"workload": w["name"], "candidates_per_gpu": w["N"], "d": w["d"], "samples": w["S"],
+           "rff_features": w["L"], "train_points": w["n"], "kernel": w["kernel"], "noise": w["noise"],
+           "reduction": {"levelset": "threshold mask + count + arg max per sample", "topk": f"top-{w.get('k')} per sample",
+                         "subset": f"values + greedy subset select (k={w.get('k')}, B={w.get('B')} noise draws)",
+                         "argmax": "max + arg max per sample (ES population scoring)"}[w["op"]],
+           "sharding": f"candidate rows over {gpus} GPU(s), no collective"}
+    if wl == "c2":
+        cfg.update(grid=f"{GRID}x{GRID} per GPU", threshold_quantile=TAU_Q)
+    in_bytes = w["N"] * w["d"] * 4
+    cfg["l2"] = ("inputs larger than L2 (%d MB X* per pass); no flush" % (in_bytes >> 20) if in_bytes > L2_BYTES
+                 else "inputs smaller than L2: a 256 MB buffer is written between timed iterations")
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------
@@ -116,50 +203,199 @@ class Clocks:
 
 
 # ------------------------------------------------------------------------------------------
-# CPU reference path: the oracle's restatement of the reference flow (fp64, one fresh basis
-# per sample, eval_in_batch chunks of 100, samples in series) on the host cores
+# roofline: per-candidate work on every pipe, the pipe that binds, and the
+# fraction T_roofline / T_measured
 # ------------------------------------------------------------------------------------------
-def cpu_reference_pass(n_rows, n_samples, seed=0):
-    """One bounded sample of the workload through the reference-style CPU path.
-    Returns (evals, seconds) of evaluate + reduce; parameter draws are not timed."""
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def roofline(wl, engine, kern_s, rows, with_mask, traffic=None, kernel_name=""):
+    """T = max over pipes of (algorithmic work per candidate / pipe peak), for the better of the two
+    admissible mappings of the feature arguments omega.x + b (FFMA, or 3xTF32 tensor-core MMAs);
+    `achieved` = frac x peak of the binding pipe.  Work per candidate (shared basis):
+      tensor : 2 (L + n) S flop                         peak = bf16 / 3 (three split products per FMA)
+               (+ 2 (d + 1) L flop at bf16 / 6 when the arguments are MMAs)
+      MUFU   : L cos + n exp (+ n sqrt for Matern)      peak = #SM x 16 / clk at the max SM clock
+      FFMA   : L (2d + 2) + n (3d + 8) + 8 (L + n) flop  peak = #SM x 128 x 2 / clk
+      HBM    : 4 d bytes (+ S / 8 for the bit mask)      peak = measured copy bandwidth"""
+    w = WORKLOADS[wl]
+    Lf, n, Sx, d = w["L"], w["n"], w["S"], w["d"]
+    pk = load_peaks()
+    bf16 = float(pk.get("bf16_tflops", 1590.0)) * 1e12
+    hbm = float(pk.get("hbm_gbps", 6500.0)) * 1e9
+    which = "MEASURED_PEAKS.json (bf16 burst, hbm copy)" if pk else "fallback 1590 TF bf16 / 6500 GB/s (B200_PROFILING.md)"
+    clk, sms = 1.965e9, 148
+    split = 6.0 if engine == "tensor_tf32x3" else 3.0
+    p_tensor, p_tf32x3 = bf16 / split, bf16 / 6.0
+    p_mufu, p_ffma = sms * 16 * clk, sms * 128 * 2 * clk
+    sfu = Lf + n * (2 if w["kernel"].startswith("matern") else 1)
+    contract = 2.0 * (Lf + n) * Sx
+    proj = 2.0 * (d + 1) * Lf
+    ffma_all = Lf * (2 * d + 2) + n * (3 * d + 8) + 8.0 * (Lf + n)
+    bytes_c = 4.0 * d + (Sx / 8.0 if with_mask else 0.0)
+    maps = {
+        "ffma arguments": {"tensor": contract / p_tensor, "mufu": sfu / p_mufu, "ffma": ffma_all / p_ffma,
+                           "hbm": bytes_c / hbm},
+        "tensor arguments": {"tensor": contract / p_tensor + proj / p_tf32x3, "mufu": sfu / p_mufu,
+                             "ffma": (ffma_all - Lf * (2 * d + 2)) / p_ffma, "hbm": bytes_c / hbm},
+    }
+    best = min(maps, key=lambda m: max(maps[m].values()))
+    pipes = maps[best]
+    bound = max(pipes, key=pipes.get)
+    t_roof = pipes[bound] * rows
+    frac = t_roof / kern_s
+    peak, unit = {"tensor": (p_tensor / 1e12, "TFLOP/s"), "mufu": (p_mufu / 1e12, "Tops/s"),
+                  "ffma": (p_ffma / 1e12, "TFLOP/s"), "hbm": (hbm / 1e9, "GB/s")}[bound]
+    return {"bound": bound, "achieved": frac * peak, "peak": peak, "unit": unit, "frac": frac, "traffic": traffic,
+            "kernel": kernel_name, "kernel_ms": 1e3 * kern_s, "roofline_ms": 1e3 * t_roof,
+            "pipes_ms": {k: 1e3 * v * rows for k, v in pipes.items()}, "mapping": best,
+            "algorithmic": {"contraction_flop_per_candidate": contract, "mufu_ops_per_candidate": sfu,
+                            "ffma_flop_per_candidate": ffma_all, "hbm_bytes_per_candidate": bytes_c},
+            "note": (f"frac = roofline time of the binding pipe / measured kernel time; tensor peak = bf16 / {split:.0f} "
+                     f"(three split-product MMAs per algorithmic FMA; TF32 runs at bf16 / 2); MUFU / FFMA peaks at the "
+                     f"{clk / 1e6:.0f} MHz max SM clock; {which}")}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (the oracle; test infrastructure used here only as the timed baseline)
+# ------------------------------------------------------------------------------------------
+def _oracle_gp(wl):
     from oracle import psbax_oracle as O
 
-    Xt, y, ls, tau = problem()
-    gp = O.GPState(train_X=Xt, train_Y=y, lengthscale=ls, outputscale=1.0, noise=NOISE, kernel=KERNEL)
+    w = WORKLOADS[wl]
+    Xt, y, ls, tau = problem_for(wl)
+    return O, O.GPState(train_X=Xt, train_Y=y, lengthscale=ls, outputscale=1.0, noise=w["noise"], kernel=w["kernel"]), tau
+
+
+def _cpu_rows(wl, n_rows):
+    w = WORKLOADS[wl]
+    if wl == "c2":
+        from oracle import psbax_oracle as O
+
+        steps = int(math.ceil(math.sqrt(n_rows)))
+        return O.reshape_mesh(O.get_mesh(2, steps))[:n_rows]
+    g = torch.Generator().manual_seed(1234)
+    X = torch.randn(n_rows, w["d"], dtype=torch.float64, generator=g) if wl == "c3" else \
+        torch.rand(n_rows, w["d"], dtype=torch.float64, generator=g)
+    return X
+
+
+def cpu_reference_pass(n_rows, n_samples, seed=0, wl="c2"):
+    """One bounded sample of the workload through the reference-style CPU path: fp64, a fresh RFF basis per
+    path (botorch get_gp_samples form), eval_in_batch chunks of 100 rows, samples in series, then the
+    algorithm's reduction.  Returns (evals, seconds) of evaluate + reduce; parameter draws are not timed."""
+    O, gp, tau = _oracle_gp(wl)
+    w = WORKLOADS[wl]
     gen = torch.Generator().manual_seed(seed)
-    p = O.draw_reference_paths(gp, n_samples, L=L, generator=gen)
-    steps = int(math.ceil(math.sqrt(n_rows)))
-    X = O.reshape_mesh(O.get_mesh(2, steps))[:n_rows]
+    p = O.draw_reference_paths(gp, n_samples, L=w["L"], generator=gen)
+    X = _cpu_rows(wl, n_rows)
+    etas = torch.randn(w["B"], n_rows, dtype=torch.float64, generator=gen).numpy() if w["op"] == "subset" else None
     t0 = time.perf_counter()
     for s in range(n_samples):
         f = O.make_callable(p, s)
-        fx = O.eval_in_batch(f, X.unsqueeze(1)).detach().numpy().flatten()  # levelset.py:26-29
-        O.levelset_reduce(fx, tau)
+        fx = O.eval_in_batch(f, X.unsqueeze(1)).detach()  # topk.py:48-49 / levelset.py:26-29
+        if w["op"] == "levelset":
+            O.levelset_reduce(fx.numpy().flatten(), tau)
+        elif w["op"] == "topk":
+            O.topk_reduce(fx, w["k"])
+        elif w["op"] == "subset":
+            O.subset_select_reduce(fx.numpy(), etas, w["k"])
+        else:
+            fx.max(0)
     return n_rows * n_samples, time.perf_counter() - t0
+
+
+def cpu_best_effort_pass(n_rows, wl="c2", seed=0):
+    """The "best-effort CPU" line: fp32, shared basis, all S paths at once, one
+    blocked GEMM pair per 64k rows on all host threads, then a vectorised reduction."""
+    O, gp, tau = _oracle_gp(wl)
+    w = WORKLOADS[wl]
+    gen = torch.Generator().manual_seed(seed)
+    p = O.draw_matheron_paths(gp, w["S"], L=w["L"], generator=gen)
+    X = _cpu_rows(wl, n_rows).to(torch.float32)
+    etas = torch.randn(w["B"], n_rows, dtype=torch.float32, generator=gen) if w["op"] == "subset" else None
+    t0 = time.perf_counter()
+    fx = O.eval_paths_best_effort(p, X)
+    if w["op"] == "levelset":
+        m = fx > (0.0 if tau is None else tau)
+        m.sum(0), fx.max(0)
+    elif w["op"] == "topk":
+        torch.topk(fx, w["k"], dim=0)
+    elif w["op"] == "subset":  # greedy over all paths, vectorised over (path, candidate), blocked over noise draws
+        cur = None
+        for _ in range(w["k"]):
+            acc = torch.zeros_like(fx)
+            for b in range(w["B"]):
+                v = fx + etas[b][:, None]
+                acc += v if cur is None else torch.maximum(v, cur[b][None, :])
+            pick = acc.argmax(0)
+            vals = fx.gather(0, pick[None])[0][None, :] + etas[:, pick]  # [B, S]
+            cur = vals if cur is None else torch.maximum(cur, vals)
+    else:
+        fx.max(0)
+    return n_rows * w["S"], time.perf_counter() - t0
+
+
+CPU_SAMPLE = {"c2": (200_000, 4), "c3": (149_361, 4), "c4": (2_000, 4), "c5": (200_000, 4)}
+CPU_BEST_ROWS = {"c2": 262_144, "c3": 149_361, "c4": 17_176, "c5": 262_144}
+
+
+def cpu_lines(wl, budget_s=12.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_rows, n_samples = CPU_SAMPLE[wl]
+    cpu_reference_pass(min(5_000, n_rows), 1, wl=wl)
+    ev = se = 0.0
+    i = 0
+    while se < budget_s:
+        e, t = cpu_reference_pass(n_rows, n_samples, seed=i, wl=wl)
+        ev, se, i = ev + e, se + t, i + 1
+    ref = {"value": ev / se, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": (f"{int(ev)} evals in {se:.1f} s: passes of {n_rows} rows x {n_samples} paths, oracle restatement "
+                      f"of the reference flow (fp64, fresh RFF basis per path, chunks of 100 rows, samples in series), "
+                      f"{torch.get_num_threads()} torch threads")}
+    rows = CPU_BEST_ROWS[wl]
+    cpu_best_effort_pass(min(rows, 65_536), wl)
+    ev = se = 0.0
+    while se < budget_s / 2:
+        e, t = cpu_best_effort_pass(rows, wl)
+        ev, se = ev + e, se + t
+    best = {"value": ev / se, "unit": UNIT, "cores": cores, "kind": "port (best effort)",
+            "sample": (f"{int(ev)} evals in {se:.1f} s: passes of {rows} rows x {WORKLOADS[wl]['S']} paths, fp32, shared "
+                       f"basis, one blocked GEMM pair per 65,536 rows + vectorised reduction, "
+                       f"{torch.get_num_threads()} torch threads")}
+    return ref, best
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    wl = args.workload
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n_rows, n_samples = 200_000, 4
+    n_rows, n_samples = CPU_SAMPLE[wl]
     for _ in range(args.warmup):
-        cpu_reference_pass(5_000, 1)
+        cpu_reference_pass(min(5_000, n_rows), 1, wl=wl)
     evals = secs = 0.0
     for i in range(args.steps):
-        e, t = cpu_reference_pass(n_rows, n_samples, seed=i)
+        e, t = cpu_reference_pass(n_rows, n_samples, seed=i, wl=wl)
         evals += e
         secs += t
     value = evals / secs
-    sample = (f"{n_rows} grid rows x {n_samples} paths per step, fp64, fresh RFF basis per path, "
+    sample = (f"{n_rows} rows x {n_samples} paths per step, fp64, fresh RFF basis per path, "
               f"chunks of 100 rows, {torch.get_num_threads()} torch threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args.gpus),
+        "data": "synthetic", "config": workload_config(wl, args.gpus),
+        "sampler": "botorch get_gp_samples form: fresh RFF basis per path, weight-space posterior draw (oracle port)",
+        "engine": "cpu (torch fp64)",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -168,176 +404,371 @@ def run_reference(args):
     return 0
 
 
-def workload_config(gpus):
-    return {"workload": "level-set on a dense 2-D grid (BASELINE configs[1])",
-            "candidates_per_gpu": GRID * GRID, "grid": f"{GRID}x{GRID} per GPU", "d": D, "samples": S,
-            "rff_features": L, "train_points": NTRAIN, "kernel": KERNEL, "threshold_quantile": TAU_Q,
-            "sampler": "matheron (shared basis + exact-kernel update)",
-            "sharding": f"candidate rows over {gpus} GPU(s), no collective",
-            "l2": "inputs larger than L2 (134 MB X* + 134 MB mask per pass); no flush"}
-
-
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch.distributed as dist
+class Ctx:
+    """Process-group plumbing shared by the legs."""
 
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.numa = bind_to_gpu_numa_node(self.local) if self.world > 1 else None
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self._flush = None
+
+    def sync_all(self):
+        torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(self, vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def flush_l2(self):
+        if self._flush is None:
+            self._flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self._flush.zero_()
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def timed_steps(ctx, step, K, flush=False):
+    """K steps, each bracketed by CUDA events on the launching stream; barrier + synchronize on both
+    sides.  Returns (span seconds [first start .. last end, minus flushes when flushing], per-step ms list)."""
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ctx.sync_all()
+    t0 = time.perf_counter()
+    out = None
+    for a, b in evs:
+        if flush:
+            ctx.flush_l2()
+        a.record()
+        out = step()
+        b.record()
+    ctx.sync_all()
+    wall = time.perf_counter() - t0
+    ms = [a.elapsed_time(b) for a, b in evs]
+    span = sum(ms) / 1e3 if flush else evs[0][0].elapsed_time(evs[-1][1]) / 1e3
+    return span, ms, wall, out
+
+
+def draw_paths(wl, dev, engine):
     from psbax_b200.models import SingleTaskGP
     from psbax_b200.sample_paths import draw_matheron_paths
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    numa = bind_to_gpu_numa_node(local) if world > 1 else None
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    N = GRID * GRID
+    w = WORKLOADS[wl]
+    Xt, y, ls, tau = problem_for(wl)
+    model = SingleTaskGP(Xt, y, kernel=w["kernel"], lengthscale=ls, outputscale=1.0, noise=w["noise"])
+    times = []
+    for _ in range(2):  # cold (first cuSOLVER / cuBLAS call of the process) and warm
+        gen = torch.Generator(device=dev).manual_seed(0)  # identical parameters on every rank
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        paths = draw_matheron_paths(model, w["S"], w["L"], generator=gen, device=dev, engine=engine)
+        torch.cuda.synchronize()
+        times.append(1e3 * (time.perf_counter() - t0))
+    return paths, tau, times
+
+
+def strict_check(paths, X, rows=4096):
+    """max |f_gpu - f_oracle| / (1e-4 * path magnitude) on a sample of this run's own rows and
+    parameters (float64 oracle on the host; the strict tolerance of tests/test_gpu_bench_parity.py)."""
+    from oracle import psbax_oracle as O
+
+    idx = torch.linspace(0, X.shape[0] - 1, rows, device=X.device).long()
+    Xs = X[idx]
+    got = paths.values(Xs).double().cpu()
+    f64 = lambda t: None if t is None else t.double().cpu()  # noqa: E731
+    p = O.PathParams(omega=f64(paths.omega), bias=f64(paths.bias), W=f64(paths.W), kernel=paths.kernel,
+                     Xtrain=f64(paths.Xtrain), inv_ls=f64(paths.inv_ls), V=f64(paths.V),
+                     mean_const=float(np.float32(paths.mean_const)), y_mean=float(np.float32(paths.y_mean)),
+                     y_std=float(np.float32(paths.y_std)))
+    ref = O.eval_paths(p, Xs.double().cpu())
+    tol = 1e-4 * O.path_scale(p)
+    return float(((got - ref).abs().max(0).values / tol).max())
+
+
+def run_ours(args):
+    ctx = Ctx()
+    wl = args.workload
+    w = WORKLOADS[wl]
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    N, Sx = w["N"], w["S"]
     K, Wm = args.steps, max(args.warmup, 3)
 
-    Xt, y, ls, tau = problem()
-    model = SingleTaskGP(Xt, y, kernel=KERNEL, lengthscale=ls, outputscale=1.0, noise=NOISE)
-    gen = torch.Generator(device=dev).manual_seed(0)  # identical parameters on every rank
-    t_draw0 = time.perf_counter()
-    paths = draw_matheron_paths(model, S, L, generator=gen, device=dev, engine=args.engine)
-    torch.cuda.synchronize()
-    t_draw = time.perf_counter() - t_draw0
-    X = grid_slab(rank, world, dev)
+    paths, tau, draw_ms = draw_paths(wl, dev, args.engine)
+    X = candidates_for(wl, rank, world, dev)
     row_offset = rank * N
+    flush = N * w["d"] * 4 <= L2_BYTES
+    etas = None
+    if w["op"] == "subset":
+        etas = torch.randn(w["B"], N, generator=torch.Generator().manual_seed(5)).to(dev)
 
-    def step():
-        return paths.levelset(X, tau, want_mask=True, row_offset=row_offset)
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+    # ---- the step: device-resident inputs, fused evaluate + reduce ----
+    if w["op"] == "levelset":
+        step = lambda: paths.levelset(X, tau, want_mask=True, row_offset=row_offset)  # noqa: E731
+        launches, kname, with_mask = 2, "fused evaluate + level-set kernel (+3 us finalize)", True
+    elif w["op"] == "topk":
+        step = lambda: paths.topk(X, w["k"], row_offset=row_offset)  # noqa: E731
+        launches, kname, with_mask = 3, "fused evaluate + top-k kernel (+ threshold seed, list merge)", False
+    elif w["op"] == "argmax":
+        step = lambda: paths.argmax(X, row_offset=row_offset)  # noqa: E731
+        launches, kname, with_mask = 2, "fused evaluate + arg-max kernel (+ finalize)", False
+    else:
+        step = lambda: paths.subset_select(X, etas, w["k"])  # noqa: E731
+        launches, kname, with_mask = 2, "evaluate (values) kernel; greedy subset-select kernel timed beside it", False
 
     for _ in range(Wm):
         res = step()
-    sync_all()
-    clocks = Clocks(local)
+    ctx.sync_all()
+    clocks = Clocks(ctx.local)
     if rank == 0:
         clocks.start()
         time.sleep(0.3)
-    # ---- device-resident timing: K steps, per-step CUDA events on the launching stream ----
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    sync_all()
     w0 = time.time()
-    t0 = time.perf_counter()
-    for a, b in evs:
-        a.record()
-        res = step()
-        b.record()
-    sync_all()
-    t_wall = time.perf_counter() - t0
+    span, kern_ms, wall, res = timed_steps(ctx, step, K, flush)
+
+    # ---- end to end through the public API with HOST buffers ----
+    e2e = {}
+    if w["op"] == "levelset":
+        e2e = e2e_levelset(ctx, paths, tau, X, row_offset, K, res)
+    else:
+        Xh = X.cpu().pin_memory()
+        xd = torch.empty_like(X)
+        eh = etas.cpu().pin_memory() if etas is not None else None
+        ed = torch.empty_like(etas) if etas is not None else None
+
+        def e2e_step():
+            xd.copy_(Xh, non_blocking=True)
+            if w["op"] == "topk":
+                v, i = paths.topk(xd, w["k"], row_offset=row_offset)
+                return v.cpu(), i.cpu()
+            if w["op"] == "argmax":
+                v, i = paths.argmax(xd, row_offset=row_offset)
+                return v.cpu(), i.cpu()
+            ed.copy_(eh, non_blocking=True)
+            return (paths.subset_select(xd, ed, w["k"]).cpu(),)
+
+        e2e_step()
+        ctx.sync_all()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            outs = e2e_step()
+        ctx.sync_all()
+        t_e2e = time.perf_counter() - t0
+        (t_e2e,) = ctx.max_over_ranks([t_e2e])
+        e2e = {"value": N * Sx * world * K / t_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": X.numel() * 4 + (etas.numel() * 4 if etas is not None else 0),
+               "d2h_bytes_per_step": sum(o.numel() * o.element_size() for o in outs),
+               "ms_per_step": 1e3 * t_e2e / K, "mode": "X* (pinned host) in, reduction result out"}
     w1 = time.time()
-    kern_ms = [a.elapsed_time(b) for a, b in evs]
-    span_ms = evs[0][0].elapsed_time(evs[-1][1])
-    # ---- end to end: host buffers through the public streaming API.  Every step uploads the
-    # rank's X* from pinned host memory and downloads the mask + counts; uploads, kernels and
-    # downloads of successive 2M-row chunks overlap on three streams. ----
-    Xh = X.cpu().pin_memory()
-    words = (N + 31) // 32
-
-    def e2e_step():
-        return paths.levelset_streamed(Xh, tau, chunk_rows=int(os.environ.get("PSBAX_E2E_CHUNK", 1 << 21)), row_offset=row_offset)
-
-    e2e_step()
-    sync_all()
-    e0 = time.perf_counter()
-    for _ in range(K):
-        masks_h, _b, cnt_h, _bv, _bi = e2e_step()
-    sync_all()
-    t_e2e = time.perf_counter() - e0
-    w1 = time.time()  # clocks are sampled over both timed loops (device-resident and end-to-end)
-    assert int(cnt_h[0]) == int(res.count[0]), "streamed and resident level sets disagree"
     clk = clocks.stop(w0, w1) if rank == 0 else None
 
-    # max over ranks
-    tt = torch.tensor([span_ms / 1e3, t_wall, t_e2e, sum(kern_ms) / 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_dev, t_wall_max, t_e2e_max, t_kern = tt.tolist()
-    counts = res.count.cpu().tolist()
+    span, wall, kern = ctx.max_over_ranks([span, wall, sum(kern_ms) / 1e3])
+    extra = {}
+    if w["op"] == "subset":  # split the step: values kernel alone (the roofline's kernel) and the greedy kernel
+        sv, _, _, fx = timed_steps(ctx, lambda: paths.values(X), K, flush)
+        kern_values = sv / K
+        extra["values_ms"] = 1e3 * kern_values
+        extra["greedy_ms"] = 1e3 * (kern / K - kern_values)
+        extra["values_only_evals_per_s"] = N * Sx / kern_values
+    if world > 1 and wl == "c2":
+        extra["topk_collective"] = leg_topk_collective(ctx, K)
+    if wl == "c2":
+        extra["strong"] = leg_strong(ctx, paths, tau, K)
+    chk = {}
+    if rank == 0:
+        chk["max_err_over_tol_strict"] = strict_check(paths, X if w["op"] != "subset" else X)
+        if w["op"] == "levelset":
+            c0 = int(res.count[0])
+            chk.update(count_s0=c0, frac_above_s0=c0 / N)
 
     if rank == 0:
-        evals_step = N * S * world
-        value = evals_step * K / t_dev
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
         eng = paths_engine(paths)
-        bf16 = peaks.get("bf16_tflops", 1590.0)
-        which = "measured (MEASURED_PEAKS.json bf16_tflops burst)" if peaks else "fallback 1590 TF bf16"
-        # three MMAs per algorithmic FMA.  BF16x3: peak = bf16 / 3;  3xTF32: TF32 dense = bf16 / 2 -> bf16 / 6
-        peak_tf = bf16 / (3.0 if eng == "tensor_bf16x3" else 6.0)
-        flops_launch = 2.0 * (L + NTRAIN) * S * N  # algorithmic, per launch (per GPU)
-        kern_s = (t_kern / K)
-        achieved = flops_launch / kern_s / 1e12
-        cpu = None
+        kern_s = extra["values_ms"] / 1e3 if w["op"] == "subset" else kern / K
+        traffic = 224.2e6 if (wl == "c2" and eng.startswith("tensor_bf16x3")) else None
+        cpu = best = None
         if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            cpu_reference_pass(5_000, 1)
-            ev = se = 0.0
-            n_rows, n_samples = 200_000, 4
-            while se < 12.0:
-                e, t = cpu_reference_pass(n_rows, n_samples, seed=int(ev) % 97)
-                ev += e
-                se += t
-            cpu = {"value": ev / se, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": (f"{int(ev)} evals in {se:.1f} s: passes of {n_rows} grid rows x {n_samples} paths, "
-                              f"oracle restatement of the reference flow (fp64, fresh RFF basis per path, "
-                              f"chunks of 100 rows, samples in series), {torch.get_num_threads()} torch threads")}
+            cpu, best = cpu_lines(wl)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"simt": "f32", "tensor_tf32x3": "f32 (3xTF32 split, fp32 accumulate)",
-                                           "tensor_bf16x3": "f32 (BF16x3 split, fp32 accumulate)"}[eng],
-            "data": "synthetic", "config": dict(workload_config(world), engine=eng,
-                                                **({"numa_node_rank0": numa} if numa is not None else {})),
-            "e2e": {"value": evals_step * K / t_e2e_max, "unit": UNIT,
-                    "h2d_bytes_per_step": N * D * 4, "d2h_bytes_per_step": S * words * 4 + S * 16,
-                    "ms_per_step": 1e3 * t_e2e_max / K},
-            "gpu_launches": 2 * K,  # per step: fused evaluate+level-set kernel + finalize (device-resident loop)
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, one
-                         # ncu --set full capture (profiles/r01_ncu_bench_kernel_bf16x3_details.csv);
-                         # algorithmic bytes = 134.2 MB X* + 134.2 MB mask
-                         "traffic": 224.2e6 if eng == "tensor_bf16x3" else None,
-                         "kernel": "fused evaluate+level-set kernel (+3 us finalize)",
-                         "kernel_ms": 1e3 * kern_s,
-                         "note": (f"algorithmic flops = 2*(L+n)*S per candidate = {2 * (L + NTRAIN) * S}; "
-                                  f"peak = bf16 {bf16} TF/s / {3 if eng == 'tensor_bf16x3' else 6} "
-                                  f"(three split-product MMAs per algorithmic FMA; TF32 runs at bf16/2), {which}")},
-            "cpu_baseline": cpu,
-            "clocks": clk,
-            "wall_ms_per_step": 1e3 * t_wall_max / K,
-            "param_draw_ms": 1e3 * t_draw,
-            "check": {"count_s0": counts[0], "frac_above_s0": counts[0] / N},
+            "metric": METRIC, "value": N * Sx * world * K / span, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": 1e3 * span / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": DTYPES[eng], "data": "synthetic",
+            "config": workload_config(wl, world),
+            "sampler": "matheron: shared RFF basis + exact-kernel update (north-star form)", "engine": eng,
+            "e2e": e2e, "gpu_launches": launches * K,
+            "roofline": roofline(wl, eng, kern_s, N, with_mask, traffic, kname),
+            "cpu_baseline": cpu, "cpu_best_effort": best, "clocks": clk,
+            "wall_ms_per_step": 1e3 * wall / K,
+            "param_draw_ms": {"cold": draw_ms[0], "warm": draw_ms[1]},
+            "check": chk,
         }
+        if ctx.numa is not None:
+            line["numa_node_rank0"] = ctx.numa
+        line.update(extra)
         print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.close()
     return 0
 
 
+def e2e_levelset(ctx, paths, tau, X, row_offset, K, res):
+    """Two end-to-end forms of the level-set step, both with HOST buffers in and out every step:
+    (1) `e2e` proper — what gen_posterior_sampling_batch consumes (posterior_sampling.py:64-81): the
+        candidate set is a mesh (src/utils.py:264-286), described by its axes (pinned host -> device
+        every step), and the result is the pooled OR-mask + per-sample counts / max / arg max
+        (device -> pinned host every step): N / 8 bytes instead of 2 x 134 MB;
+    (2) `full_mask` — X* rows uploaded from pinned host memory and all S bit masks downloaded
+        (levelset_streamed: uploads, kernels and downloads of 2M-row chunks overlap on three streams)."""
+    N, Sx, world, rank, dev = X.shape[0], paths.S, ctx.world, ctx.rank, ctx.dev
+    a0h, a1h = (a.pin_memory() for a in grid_axes(world))
+    a0d, a1d = torch.empty_like(a0h, device=dev), torch.empty_like(a1h, device=dev)
+    words = (N + 31) // 32
+    pooled_h = torch.empty(words, dtype=torch.int32).pin_memory()
+    cnt_h = torch.empty(Sx, dtype=torch.int64).pin_memory()
+    mx_h = torch.empty(Sx, dtype=torch.float32).pin_memory()
+    am_h = torch.empty(Sx, dtype=torch.int64).pin_memory()
+
+    def mesh_step():
+        a0d.copy_(a0h, non_blocking=True)
+        a1d.copy_(a1h, non_blocking=True)
+        r = paths.levelset(None, tau, want_mask=False, want_pooled=True, row_offset=row_offset, mesh=[a0d, a1d], N=N)
+        pooled_h.copy_(r.pooled, non_blocking=True)
+        cnt_h.copy_(r.count, non_blocking=True)
+        mx_h.copy_(r.maxval, non_blocking=True)
+        am_h.copy_(r.argmax, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the result on the host every step
+        return r
+
+    mesh_step()
+    ctx.sync_all()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        mesh_step()
+    ctx.sync_all()
+    t_mesh = time.perf_counter() - t0
+    assert torch.equal(cnt_h, res.count.cpu()), "mesh-descriptor and uploaded-rows level sets disagree"
+
+    Xh = X.cpu().pin_memory()
+
+    def full_step():
+        return paths.levelset_streamed(Xh, tau, chunk_rows=int(os.environ.get("PSBAX_E2E_CHUNK", 1 << 21)),
+                                       row_offset=row_offset)
+
+    full_step()
+    ctx.sync_all()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        _m, _b, cnt_f, _bv, _bi = full_step()
+    ctx.sync_all()
+    t_full = time.perf_counter() - t0
+    assert int(cnt_f[0]) == int(res.count[0]), "streamed and resident level sets disagree"
+    t_mesh, t_full = ctx.max_over_ranks([t_mesh, t_full])
+    ev = N * Sx * world * K
+    return {"value": ev / t_mesh, "unit": UNIT,
+            "h2d_bytes_per_step": (a0h.numel() + a1h.numel()) * 4, "d2h_bytes_per_step": words * 4 + Sx * 20,
+            "ms_per_step": 1e3 * t_mesh / K,
+            "mode": "mesh axes (pinned host) in; pooled OR-mask + counts / max / arg max (pinned host) out",
+            "full_mask": {"value": ev / t_full, "unit": UNIT, "h2d_bytes_per_step": N * paths.d * 4,
+                          "d2h_bytes_per_step": Sx * words * 4 + Sx * 16, "ms_per_step": 1e3 * t_full / K,
+                          "mode": "X* rows (pinned host) in; all S bit masks + counts (pinned host) out, streamed"}}
+
+
+def leg_topk_collective(ctx, K):
+    """The path's one real exchange step (psbax_b200/distributed.py): the c3
+    candidate set sharded by rows over the ranks; per step each rank runs the fused top-k on its
+    shard, then ONE NCCL all-gather of the [S, k] (value, global index) lists and the same
+    deterministic merge on every rank, all on one stream.  Asserted bit-identical to the unsharded
+    launch.  Strong scaling (N = 149,361 in total)."""
+    from psbax_b200 import distributed as D
+
+    w = WORKLOADS["c3"]
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    paths, _tau, _ = draw_paths("c3", dev, "auto")
+    Xall = candidates_for("c3", 0, 1, dev)  # same rows on every rank (seeded)
+    lo, hi = D.my_shard(w["N"], rank, world)
+    Xloc = Xall[lo:hi].contiguous()
+    k = w["k"]
+
+    def step():
+        return D.topk_sharded(lambda kk: paths.topk(Xloc, kk, row_offset=lo), k, hi - lo)
+
+    def gather_only(v, i):
+        return D.all_gather_lists(v, i)
+
+    for _ in range(3):
+        val, idx = step()
+    full_v, full_i = paths.topk(Xall, k)
+    assert torch.equal(idx, full_i) and torch.equal(val, full_v), "sharded top-k differs from the unsharded launch"
+    span, ms, _wall, _ = timed_steps(ctx, step, K, flush=True)
+    lv, li = paths.topk(Xloc, k, row_offset=lo)
+    gspan, _gms, _, _ = timed_steps(ctx, lambda: gather_only(lv, li), K, flush=False)
+    one, _oms, _, _ = timed_steps(ctx, lambda: paths.topk(Xall, k), K, flush=True)
+    span, gspan, one = ctx.max_over_ranks([span, gspan, one])
+    return {"workload": w["name"], "candidates_total": w["N"], "samples": w["S"], "k": k, "scaling": "strong",
+            "ms_per_step": 1e3 * span / K, "evals_per_s": w["N"] * w["S"] * K / span,
+            "allgather_ms_per_step": 1e3 * gspan / K, "allgather_bytes_per_rank": w["S"] * k * 16,
+            "one_gpu_unsharded_ms": 1e3 * one / K, "bit_identical_to_unsharded": True, "ranks": world}
+
+
+def leg_strong(ctx, paths, tau, K):
+    """Strong scaling of the c2 level set: a 3163 x 3163 grid (1.0e7 rows) split by
+    rows over the ranks (mesh descriptor; mask + pooled written), no collective."""
+    from psbax_b200 import distributed as D
+
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
+    ax = torch.linspace(0, 1, STRONG_STEPS, dtype=torch.float64).to(torch.float32).to(dev)
+    Ntot = STRONG_STEPS * STRONG_STEPS
+    lo, hi = D.my_shard(Ntot, rank, world)
+    lo = (lo // 32) * 32 if rank else 0  # shard boundaries on mask-word boundaries
+    hi = (hi // 32) * 32 if rank < world - 1 else Ntot
+
+    def step():
+        return paths.levelset(None, tau, want_mask=True, want_pooled=True, row_offset=lo, mesh=[ax, ax], N=hi - lo)
+
+    for _ in range(3):
+        r = step()
+    span, _ms, _wall, r = timed_steps(ctx, step, K, flush=False)
+    (span,) = ctx.max_over_ranks([span])
+    cnt = r.count.clone()
+    if world > 1:
+        ctx.dist.all_reduce(cnt)
+    return {"candidates_total": Ntot, "samples": paths.S, "scaling": "strong", "ms_per_step": 1e3 * span / K,
+            "evals_per_s": Ntot * paths.S * K / span, "count_s0_total": int(cnt[0]), "ranks": world}
+
+
+DTYPES = {"simt": "f32 (FFMA + MUFU)",
+          "tensor_tf32x3": "f32 (3xTF32 operand split on every feature block, fp32 accumulate)",
+          "tensor_bf16x3": "f32 (RFF blocks: BF16x3 operand split; exact-kernel blocks: 3xTF32 split; fp32 accumulate)",
+          "tensor_bf16x3_proj": ("f32 (feature arguments: 3xTF32 MMAs; RFF blocks: BF16x3 split; exact-kernel blocks: "
+                                 "3xTF32 split; fp32 accumulate)")}
+
+
 def paths_engine(paths):
-    """Which kernel family the library resolves to for this batch (mirrors make_layout)."""
-    shared = paths.G == 1 and paths.S >= 16 and paths.L > 0
+    """Which kernel family the library resolves to for this batch (mirrors make_layout in
+    psbax_b200/csrc/psbax_b200.cu: shared basis -> tensor engines unless S == 1 and d <= 4)."""
+    shared = paths.G == 1 and (paths.S >= 2 or paths.d >= 5)
     if paths.engine == "simt" or not shared:
         return "simt"
     if paths.engine == "tensor":
         return "tensor_tf32x3"
+    if paths.engine in ("auto", "tensor_proj") and 5 <= paths.d <= 32:
+        return "tensor_bf16x3_proj"
     return "tensor_bf16x3"
 
 
@@ -375,6 +806,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tensor", "tensor_bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
