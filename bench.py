@@ -543,6 +543,8 @@ def run_ours(args):
         time.sleep(0.3)
     w0 = time.time()
     span, kern_ms, wall, res = timed_steps(ctx, step, K, flush)
+    if os.environ.get("PSBAX_BENCH_DEBUG"):
+        sys.stderr.write(f"rank {rank}: per-step ms {['%.3f' % m for m in kern_ms]}\n")
 
     # ---- end to end through the public API with HOST buffers ----
     e2e = {}

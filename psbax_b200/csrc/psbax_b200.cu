@@ -351,12 +351,19 @@ int psbax_eval_levelset_ex(const psbax_paths_t* paths, const void* pack, const f
       a.mesh_axis[i] = mesh->axis[i];
       a.mesh_len[i] = (int)mesh->len[i];
       a.mesh_stride[i] = total;
+      int sh = 0;
+      while ((1LL << sh) < mesh->len[i]) ++sh;  // ceil(log2 len)
+      a.mesh_shift[i] = sh;
+      a.mesh_magic[i] = mesh->len[i] > 1 ? (unsigned int)(((1ULL << (32 + sh)) / (unsigned long long)mesh->len[i]) + 1ULL -
+                                                          (1ULL << 32)) : 0u;
       if (total > (1LL << 62) / mesh->len[i]) return fail(PSBAX_E_INVALID, "mesh too large");
       total *= mesh->len[i];
     }
     if (row_offset + N > total)
       return fail(PSBAX_E_INVALID, "rows [%lld, %lld) exceed the mesh (%lld rows)", (long long)row_offset,
                   (long long)(row_offset + N), total);
+    // rows past N inside the last tile are never generated (callers test row < N first)
+    a.mesh_fast = (row_offset + N <= 0xFFFFFFFFLL) ? 1 : 0;
   }
   const int parts = is_tensor_mode(l.mode) ? tensor_parts_any(l, N, pr.sms, EPI_LEVELSET, 0) : (int)pr.grid.x;
   const size_t per = (size_t)parts * l.Sp;

@@ -110,11 +110,35 @@ struct KArgs {
   const float* mesh_axis[4];
   long long mesh_stride[4];
   int mesh_len[4];
+  // fast path (every global row index of the call fits 32 bits): the multi-index is peeled off from the
+  // last axis with multiply-high divisions by the axis lengths, q = (t + ((g - t) >> 1)) >> (shift - 1),
+  // t = umulhi(g, magic), magic = floor(2^(32 + shift) / len) + 1 - 2^32, shift = ceil(log2 len)
+  unsigned int mesh_magic[4];
+  int mesh_shift[4];
+  int mesh_fast;
 };
+
+__device__ __forceinline__ unsigned int mesh_div(const KArgs& a, unsigned int g, int ax) {
+  if (a.mesh_len[ax] == 1) return g;
+  const unsigned int t = __umulhi(g, a.mesh_magic[ax]);
+  return (t + ((g - t) >> 1)) >> (a.mesh_shift[ax] - 1);
+}
 
 // coordinate i of local candidate row `row`: from X, or generated from the mesh axes
 __device__ __forceinline__ float load_x(const KArgs& a, long long row, int i) {
   if (a.X != nullptr) return __ldg(a.X + row * a.lay.d + i);
+  if (a.mesh_fast) {
+    unsigned int g = (unsigned int)(a.row_offset + row);
+#pragma unroll
+    for (int ax = 3; ax > 0; --ax) {
+      if (ax < a.lay.d && ax >= i) {
+        const unsigned int q = mesh_div(a, g, ax);
+        if (ax == i) return __ldg(a.mesh_axis[i] + (g - q * (unsigned int)a.mesh_len[ax]));
+        g = q;
+      }
+    }
+    return __ldg(a.mesh_axis[0] + g);  // i == 0: the slowest axis is what is left (row < prod(len))
+  }
   const long long g = a.row_offset + row;
   const int j = (int)((g / a.mesh_stride[i]) % a.mesh_len[i]);
   return __ldg(a.mesh_axis[i] + j);

@@ -109,3 +109,21 @@ def test_mesh_3d_matches_uploaded_rows():
         a = batch.levelset(X.cuda(), -0.5, want_pooled=True)
         b = batch.levelset(None, -0.5, want_pooled=True, mesh=axes)
         assert torch.equal(a.mask, b.mask) and torch.equal(a.pooled, b.pooled) and torch.equal(a.argmax, b.argmax)
+
+
+def test_mesh_rows_beyond_32_bits():
+    """Global row indices above 2^32 take the 64-bit index path; below, the multiply-high path: both must
+    generate the rows of the 'ij' mesh bit for bit."""
+    from helpers import random_params
+
+    p = random_params(8, 64, 2, 9, kernel="rbf", seed=11)
+    batch = to_batch(p, engine="auto")
+    a0, a1 = torch.rand(1 << 20), torch.rand(5000)  # 5.2e9 mesh rows; only the axes exist in memory
+    for lo in (0, 4999 * 777 + 123, (1 << 32) - 700, (1 << 32) + 12345):
+        n = 3001
+        g = torch.arange(lo, lo + n)
+        X = torch.stack([a0[g // 5000], a1[g % 5000]], dim=-1)
+        want = batch.levelset(X.cuda(), 0.0, want_pooled=True, row_offset=lo)
+        got = batch.levelset(None, 0.0, want_pooled=True, row_offset=lo, mesh=[a0, a1], N=n)
+        assert torch.equal(got.mask, want.mask) and torch.equal(got.argmax, want.argmax)
+        assert torch.equal(got.maxval, want.maxval) and torch.equal(got.count, want.count)
