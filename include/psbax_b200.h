@@ -130,6 +130,17 @@ int psbax_sumsq_scratch_bytes(const psbax_paths_t* paths, int64_t N, size_t* byt
 int psbax_eval_sumsq(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
                      float* out, void* scratch, size_t scratch_bytes, void* stream);
 
+/* Grouped form of psbax_eval_sumsq: out[g, i] = sum of f_s(X[i, :])^2 over the samples
+ * s in [g * group, (g + 1) * group), out is [ceil(S / group), N]; `group` divides 64.  One launch then
+ * yields the explained variance under SEVERAL models that share one candidate stream: the INFO-BAX
+ * expected information gain (src/acquisition_functions/bax_acquisition.py:87-122, 156-174) needs the
+ * posterior variance of the current model and of one fantasy model per execution path; by the block
+ * Cholesky identity the fantasy of path s only adds the rows [-L_s^-1 B_s L^-1, L_s^-1] to L^-1, so all
+ * of them are pseudo-paths over the union of the training set and the execution paths, one group
+ * (or a few) per model. */
+int psbax_eval_sumsq_groups(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                            int32_t group, float* out, void* stream);
+
 /* Fused evaluation + LevelSetEstimator reduction (src/algorithms/levelset.py:34-39)
  * for all S paths: mask bit (i % 32) of mask[s, i / 32] = (f_s(X[i]) > tau);
  * count[s] = popcount; maxval/argmax[s] = max and (smallest) arg max of f_s over
@@ -196,6 +207,18 @@ int psbax_subset_select(const float* fx, int64_t ld_fx, const float* etas, int64
  * (src/algorithms/lbfgsb.py:29-39).  sample_idx is int32 [N] (NULL = sample 0). */
 int psbax_eval_grad(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
                     const int32_t* sample_idx, float* val, float* grad, void* stream);
+
+/* Batched multi-start ascent: P independent box-constrained ascents on [0, 1]^d, ascent i maximising
+ * sample path sample_idx[i] from the start X0[i, :], all inside ONE launch (one CTA per ascent; projected
+ * L-BFGS with 8 curvature pairs and Armijo backtracking, value + gradient as psbax_eval_grad).  Replaces the
+ * serial scipy L-BFGS-B loop under botorch optimize_acqf that LBFGSB.run_algorithm_on_f drives
+ * (src/algorithms/lbfgsb.py:24-40, src/utils.py:120-150: num_restarts = 5 d ascents per sample path,
+ * maxiter 100): restarts x samples ascents per call.  Stops when the projected gradient's max norm is
+ * <= pgtol, the relative increase of f is <= ftol, the line search fails, or after maxiter iterations.
+ * x_out [P, d], f_out [P] (f at x_out, output units), iters [P] (may be NULL); d <= 32. */
+int psbax_ascend(const psbax_paths_t* paths, const void* pack, const float* X0, int64_t P,
+                 const int32_t* sample_idx, int32_t maxiter, float pgtol, float ftol, float* x_out,
+                 float* f_out, int32_t* iters, void* stream);
 
 #ifdef __cplusplus
 }

@@ -545,6 +545,44 @@ def entropy_acqf(gp: GPState, X: torch.Tensor) -> torch.Tensor:
     return torch.stack(out)
 
 
+def condition_on_observations(gp: GPState, X_new: torch.Tensor, Y_new: torch.Tensor) -> GPState:
+    """``BAXAcquisitionFunction.fit_with_old_model`` (``bax_acquisition.py:177-203``) -> botorch
+    ``SingleTaskGP.condition_on_observations``: the same hyper-parameters and the SAME (already
+    fitted) ``Standardize`` statistics; the new rows are observed with the likelihood noise."""
+    new = GPState(train_X=torch.cat([gp.train_X, X_new.to(DTYPE).reshape(-1, gp.d)]),
+                  train_Y=torch.cat([gp.train_Y, Y_new.to(DTYPE).reshape(-1)]), lengthscale=gp.lengthscale,
+                  outputscale=gp.outputscale, noise=gp.noise, kernel=gp.kernel, mean_const=gp.mean_const,
+                  standardize=False)
+    new.y_mean, new.y_std = gp.y_mean, gp.y_std
+    return new
+
+
+def bax_eig(gp: GPState, exe_paths, X: torch.Tensor, pending: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``BAXAcquisitionFunction.forward`` with ``acq_str="exe"`` (``bax_acquisition.py:87-122``,
+    ``acq_exe_normal`` ``:156-174``, ``entropy`` ``:142-152``): X [b, q, d] -> [b],
+
+        H[f(X)] - mean_s H[f(X) | execution path s],   H = 0.5 log(2 pi) + 0.5 logdet Cov_post(X),
+
+    the conditional models being ``condition_on_observations`` of the current one on each path's
+    (x, y) (``initialize`` ``:236-247``).  ``exe_paths`` is a list of (x [k, d], y [k]) pairs;
+    ``pending`` rows are appended to every q-batch (``@concatenate_pending_points``)."""
+    X = X.to(DTYPE)
+    if pending is not None and pending.numel() > 0:
+        X = torch.cat([X, pending.to(DTYPE).reshape(1, -1, X.shape[-1]).expand(X.shape[0], -1, -1)], dim=-2)
+    models = [condition_on_observations(gp, px, py) for px, py in exe_paths]
+
+    def entropy(g, Xb):
+        _, cov = gp_posterior(g, Xb)
+        return 0.5 * math.log(2 * math.pi) + 0.5 * torch.logdet(cov)
+
+    out = []
+    for Xb in X:
+        h_post = entropy(gp, Xb)
+        h_samp = torch.stack([entropy(m, Xb) for m in models])
+        out.append(h_post - h_samp.mean())
+    return torch.stack(out)
+
+
 def optimize_acqf_discrete(gp: GPState, choices: torch.Tensor, q: int):
     """botorch 0.10 ``optimize_acqf_discrete(unique=True)`` restated for the
     entropy acquisition: greedy over q, the chosen row joins X_pending and is

@@ -19,8 +19,8 @@ ENGINE_IDS = {"auto": 0, "simt": 1, "tensor": 2, "tensor_bf16": 3, "tensor_proj"
 # every symbol include/psbax_b200.h declares
 EXPORTS = [
     "psbax_version", "psbax_last_error", "psbax_debug_trace_buffer", "psbax_device_sms", "psbax_pack_bytes", "psbax_pack",
-    "psbax_workspace_bytes", "psbax_eval_values", "psbax_sumsq_scratch_bytes", "psbax_eval_sumsq", "psbax_eval_levelset", "psbax_eval_levelset_ex", "psbax_eval_topk",
-    "psbax_topk_merge", "psbax_subset_select", "psbax_eval_grad",
+    "psbax_workspace_bytes", "psbax_eval_values", "psbax_sumsq_scratch_bytes", "psbax_eval_sumsq", "psbax_eval_sumsq_groups", "psbax_eval_levelset", "psbax_eval_levelset_ex", "psbax_eval_topk",
+    "psbax_topk_merge", "psbax_subset_select", "psbax_eval_grad", "psbax_ascend",
 ]
 
 
@@ -64,6 +64,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.psbax_eval_values.argtypes = [P, vp, vp, i64, vp, i64, vp]
     lib.psbax_sumsq_scratch_bytes.argtypes = [P, i64, C.POINTER(C.c_size_t)]
     lib.psbax_eval_sumsq.argtypes = [P, vp, vp, i64, vp, vp, C.c_size_t, vp]
+    lib.psbax_eval_sumsq_groups.argtypes = [P, vp, vp, i64, i32, vp, vp]
     lib.psbax_eval_levelset.argtypes = [P, vp, vp, i64, i64, f32, vp, i64, vp, vp, vp, vp, sz, vp]
     lib.psbax_eval_levelset_ex.argtypes = [P, vp, vp, C.POINTER(MeshStruct), i64, i64, f32, vp, i64, vp, vp, vp, vp, vp,
                                            sz, vp]
@@ -71,6 +72,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.psbax_topk_merge.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.psbax_subset_select.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp]
     lib.psbax_eval_grad.argtypes = [P, vp, vp, i64, vp, vp, vp, vp]
+    lib.psbax_ascend.argtypes = [P, vp, vp, i64, vp, i32, f32, f32, vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name).restype = C.c_int
 

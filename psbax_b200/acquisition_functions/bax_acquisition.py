@@ -86,8 +86,55 @@ class BAXAcquisitionFunction:
 
     __call__ = forward
 
+    MAX_FUSED_ROWS = 2048  # training + pending + execution-path rows one fused launch takes as kernel features
+
     def q1_values(self, choices: torch.Tensor) -> torch.Tensor:
-        """``forward(choices.unsqueeze(-2))`` for every row of ``choices`` [m, d]: S + 1 fused launches.
+        """``forward(choices.unsqueeze(-2))`` for every row of ``choices`` [m, d] in ONE fused launch for the
+        current model and all S fantasy models (``psbax_eval_sumsq_groups`` over the pseudo-paths of
+        ``fantasy_variance_params``: the fantasy models share the Cholesky rows of the current one).
+
+        EIG(x) = 0.5 log var_0(x | P) - mean_s 0.5 log var_s(x | P) (+ the x-independent pending terms),
+        variances floored at the float32 resolution of the difference alpha - sumsq (1e-6 alpha): rows
+        whose variance the data already explain cannot win the arg max by rounding noise."""
+        from ..sample_paths import SamplePathBatch, fantasy_variance_params
+
+        choices = torch.as_tensor(choices)
+        d = choices.shape[-1]
+        path_xs = [torch.as_tensor(np.asarray(ep.x)).reshape(-1, d) for ep in self.exe_path_list]
+        pend = self.X_pending.reshape(-1, d).to(torch.float64) if self.X_pending is not None else None
+        n_pend = 0 if pend is None else pend.shape[0]
+        rows = self.model.train_inputs[0].shape[0] + n_pend + sum(p.shape[0] for p in path_xs)
+        if rows > self.MAX_FUSED_ROWS:
+            return self._q1_values_per_model(choices)
+        group = 16
+        params, g0, gs = fantasy_variance_params(self.model, path_xs, pending=pend, group=group)
+        try:
+            batch = SamplePathBatch(**params, engine="tensor")  # 3xTF32: alpha - sumsq cancels
+        except Exception as ex:
+            if "engine needs" not in str(ex):
+                raise
+            batch = SamplePathBatch(**params, engine="auto")
+        sq = batch.sumsq_groups(choices, group).double()  # [g0 + sum(gs), m]
+        alpha = float(self.model.covar_module.outputscale)
+        floor = 1e-6 * alpha
+        var0 = alpha - sq[:g0].sum(0)
+        val = 0.5 * torch.log(var0.clamp_min(floor))
+        cond = torch.zeros_like(val)
+        g = g0
+        for gk in gs:
+            cond += 0.5 * torch.log((var0 - sq[g:g + gk].sum(0)).clamp_min(floor))
+            g += gk
+        val = val - cond / len(gs)
+        if n_pend:  # the terms that do not depend on x
+            P = pend.reshape(1, -1, d)
+            const = self.entropy(self.model.posterior(P).covariance_matrix[0]) - torch.stack(
+                [self.entropy(cm.posterior(P).covariance_matrix[0]) for cm in self.comb_model_list]).mean()
+            val = val + const.to(val.device)
+        return val.to(choices.device)
+
+    def _q1_values_per_model(self, choices: torch.Tensor) -> torch.Tensor:
+        """The same numbers through S + 1 fused launches, one (n + k) x (n + k) factorisation each (kept as
+        the cross-check of ``q1_values`` and for execution paths too long for one launch).
 
         logdet Cov_M([x, P]) = logdet Cov_M(P) + log var_M(x | P) for the current model M_0 and for
         every fantasy model M_s (data + execution path s, observed with the likelihood noise), P the
@@ -114,7 +161,8 @@ class BAXAcquisitionFunction:
             else:
                 var = posterior_variance(self.model, choices, pending=torch.cat(rows),
                                          pending_noise=torch.cat(rnoise))
-            return torch.log(var.double().clamp_min(1e-300))
+            _, y_std = self.model.y_mean_std()
+            return torch.log(var.double().clamp_min(1e-6 * float(self.model.covar_module.outputscale) * float(y_std) ** 2))
 
         val = 0.5 * log_var(None)
         cond = torch.zeros_like(val)

@@ -312,6 +312,21 @@ int psbax_eval_sumsq(const psbax_paths_t* paths, const void* pack, const float* 
   return PSBAX_OK;
 }
 
+int psbax_eval_sumsq_groups(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
+                            int32_t group, float* out, void* stream) {
+  Prepared pr;
+  int rc = prepare(paths, pack, X, N, &pr);
+  if (rc) return rc;
+  if (!out) return fail(PSBAX_E_INVALID, "out is NULL");
+  if (group < 1 || group > TN || TN % group != 0)
+    return fail(PSBAX_E_INVALID, "group=%d must divide %d", group, TN);
+  pr.a.rowsq = out;
+  pr.a.rowsq_group = group;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_tensor_mode(pr.a.lay.mode)) return tensor_launch_any(EPI_VALUES, pr.a, pr.sms, st, g_err, sizeof(g_err));
+  return simt_launch(EPI_VALUES, pr.a, pr.grid, st, g_err, sizeof(g_err));
+}
+
 int psbax_eval_levelset(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
                         int64_t row_offset, float tau, uint32_t* mask, int64_t mask_ld,
                         int64_t* count, float* maxval, int64_t* argmax, void* workspace,
@@ -510,6 +525,26 @@ int psbax_eval_grad(const psbax_paths_t* paths, const void* pack, const float* X
     CUDA_TRY(cudaFuncSetAttribute(k_eval_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   k_eval_grad<<<(unsigned)N, 128, smem, st>>>(pr.a, sample_idx, val, grad);
+  CUDA_TRY(cudaGetLastError());
+  return PSBAX_OK;
+}
+
+int psbax_ascend(const psbax_paths_t* paths, const void* pack, const float* X0, int64_t P,
+                 const int32_t* sample_idx, int32_t maxiter, float pgtol, float ftol, float* x_out,
+                 float* f_out, int32_t* iters, void* stream) {
+  Prepared pr;
+  int rc = prepare(paths, pack, X0, P, &pr);
+  if (rc) return rc;
+  if (!x_out || !f_out) return fail(PSBAX_E_INVALID, "x_out / f_out is NULL");
+  if (paths->d > ASC_DMAX) return fail(PSBAX_E_UNSUPPORTED, "ascent kernel needs d <= %d (got %d)", ASC_DMAX, paths->d);
+  if (maxiter < 0) return fail(PSBAX_E_INVALID, "maxiter must be >= 0");
+  const Layout& l = pr.a.lay;
+  const size_t smem = ((size_t)2 * l.dp4 + l.Lp + l.np_ + 8) * sizeof(float);
+  if (smem > 200 * 1024) return fail(PSBAX_E_UNSUPPORTED, "L + n too large for the ascent kernel");
+  if (smem > 40 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(k_ascend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  k_ascend<<<(unsigned)P, 128, smem, st>>>(pr.a, sample_idx, x_out, f_out, iters, maxiter, pgtol, ftol);
   CUDA_TRY(cudaGetLastError());
   return PSBAX_OK;
 }

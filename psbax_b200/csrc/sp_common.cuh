@@ -89,6 +89,7 @@ struct KArgs {
   long long ld_out;
   // VALUES, row-norm variant (psbax_eval_sumsq): rowsq[chunk][N] = sum over the chunk's samples of y^2
   float* rowsq;
+  int rowsq_group;  // 0: one sum per 64-sample chunk; g (a divisor of 64): rowsq[s / g][N], one sum per g consecutive samples
   // LEVELSET
   float tau;
   uint32_t* mask;

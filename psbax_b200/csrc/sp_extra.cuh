@@ -283,4 +283,222 @@ __global__ void __launch_bounds__(128) k_eval_grad(const __grid_constant__ KArgs
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Batched multi-start ascent (LBFGSB, src/algorithms/lbfgsb.py:24-40 -> botorch optimize_acqf:
+// num_restarts L-BFGS-B ascents from the best raw samples, box [0, 1]^d, maxiter 100).
+// One CTA (128 threads) per (start, sample) pair runs the WHOLE ascent on the device: value + gradient
+// of the path by all threads (as k_eval_grad), then a projected L-BFGS step (two-loop recursion over
+// the last ASC_MEM curvature pairs on the free variables, Armijo backtracking along the projected
+// path) by thread 0 — the vector algebra is d <= 32 wide, the evaluation is L + n wide.  Every pair
+// is independent: restarts x samples CTAs in one launch instead of one launch per iterate.
+// ---------------------------------------------------------------------------------
+constexpr int ASC_MEM = 8;
+constexpr int ASC_DMAX = 32;
+
+struct AscShared {
+  float x[ASC_DMAX], xt[ASC_DMAX], g[ASC_DMAX], gt[ASC_DMAX], p[ASC_DMAX];
+  float sk[ASC_MEM][ASC_DMAX], yk[ASC_MEM][ASC_DMAX], rho[ASC_MEM];
+  float f, ft, red[4];
+  int flag;
+};
+
+// f_s(x) (output units) and d f_s / dx at the point in `xin` (shared, [d]); result -> *fout, gout[d]
+// (shared).  Called by all 128 threads; ends with a barrier.
+__device__ __forceinline__ void asc_value_grad(const KArgs& a, int s, const float* xin, float* sx, float* sxs,
+                                               float* coef, float* coefk, float* red, float* fout, float* gout) {
+  const Layout& lay = a.lay;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = lay.d, dp4 = lay.dp4;
+  const float* __restrict__ IL = a.pack + lay.off_invls;
+  for (int i = tid; i < dp4; i += blockDim.x) {
+    const float xv = (i < d) ? xin[i] : 0.f;
+    sx[i] = xv;
+    sxs[i] = xv * __ldg(IL + i);
+  }
+  __syncthreads();
+  const bool persample = lay.mode == MODE_PERSAMPLE;
+  const float* __restrict__ rows = persample ? a.pack + lay.off_pb + (size_t)s * lay.Lp * lay.OSB
+                                             : a.pack + lay.off_ft;
+  const int rs = persample ? lay.OSB : lay.OS;
+  const float* __restrict__ WV = a.pack + lay.off_wv;
+  float acc = 0.f;
+  for (int l = tid; l < lay.Lp; l += blockDim.x) {
+    const float* r = rows + (size_t)l * rs;
+    float arg = __ldg(r + dp4);
+    for (int i = 0; i < d; ++i) arg = fmaf(sx[i], __ldg(r + i), arg);
+    const float w = persample ? __ldg(r + dp4 + 1) : __ldg(WV + (size_t)l * lay.Sp + s);
+    if (l >= lay.Lcos) {
+      acc = fmaf(w, arg, acc);
+      coef[l] = w;
+    } else {
+      float sn, cs;
+      sincosf(arg, &sn, &cs);
+      acc = fmaf(w, cs, acc);
+      coef[l] = -w * sn;
+    }
+  }
+  const float* __restrict__ FTK = a.pack + lay.off_ft + (size_t)lay.kk0 * lay.OS;
+  const float* __restrict__ VT = a.pack + lay.off_wv + (size_t)lay.kk0 * lay.Sp;
+  for (int j = tid; j < lay.n; j += blockDim.x) {
+    const float* r = FTK + (size_t)j * lay.OS;
+    float r2 = 0.f;
+    for (int i = 0; i < d; ++i) {
+      const float df = sxs[i] + __ldg(r + i);
+      r2 = fmaf(df, df, r2);
+    }
+    const float v = __ldg(VT + (size_t)j * lay.Sp + s);
+    acc = fmaf(v, kernel_profile(r2, lay.kernel), acc);
+    coefk[j] = v * kernel_profile_dr2x2(r2, lay.kernel);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (tid == 0) *fout = fmaf(red[0] + red[1] + red[2] + red[3], a.ystd, a.c0);
+  // gradient: warp w takes dimensions w, w + 4, ...; lanes split the feature range
+  for (int i = warp; i < d; i += 4) {
+    float g = 0.f;
+    for (int l = lane; l < lay.Lp; l += 32) g = fmaf(coef[l], __ldg(rows + (size_t)l * rs + i), g);
+    float gk = 0.f;
+    for (int j = lane; j < lay.n; j += 32) gk = fmaf(coefk[j], sxs[i] + __ldg(FTK + (size_t)j * lay.OS + i), gk);
+    g = fmaf(gk, __ldg(IL + i), g);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) g += __shfl_xor_sync(0xffffffffu, g, off);
+    if (lane == 0) gout[i] = a.ystd * g;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(128) k_ascend(const __grid_constant__ KArgs a, const int* __restrict__ sample_idx,
+                                                float* __restrict__ xout, float* __restrict__ fout,
+                                                int* __restrict__ iters, int maxiter, float pgtol, float ftol) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ AscShared sh;
+  const Layout& lay = a.lay;
+  const int tid = threadIdx.x;
+  const long long p = blockIdx.x;
+  const int s = sample_idx ? sample_idx[p] : 0;
+  const int d = lay.d, dp4 = lay.dp4;
+  float* sx = smem;
+  float* sxs = sx + dp4;
+  float* coef = sxs + dp4;
+  float* coefk = coef + lay.Lp;
+  if (tid < d) sh.x[tid] = fminf(fmaxf(__ldg(a.X + p * d + tid), 0.f), 1.f);
+  __syncthreads();
+  asc_value_grad(a, s, sh.x, sx, sxs, coef, coefk, sh.red, &sh.f, sh.g);
+  int nmem = 0, head = 0, it = 0;  // thread 0's view of the curvature history (ring)
+  for (; it < maxiter; ++it) {
+    if (tid == 0) {
+      // ascent on f == descent on h = -f; free variables: not pinned at a bound by the gradient
+      float q[ASC_DMAX], al[ASC_MEM];
+      float pg = 0.f;
+      for (int i = 0; i < d; ++i) {
+        const float gi = sh.g[i];
+        const bool pinned = (sh.x[i] <= 0.f && gi < 0.f) || (sh.x[i] >= 1.f && gi > 0.f);
+        q[i] = pinned ? 0.f : -gi;  // gradient of h on the free set
+        pg = fmaxf(pg, fabsf(q[i]));
+      }
+      int flag = 0;
+      if (pg <= pgtol) flag = 1;  // projected gradient small: converged
+      if (!flag) {
+        for (int m = 0; m < nmem; ++m) {  // two-loop recursion, newest pair first
+          const int j = (head - 1 - m + ASC_MEM) % ASC_MEM;
+          float dt = 0.f;
+          for (int i = 0; i < d; ++i) dt = fmaf(sh.sk[j][i], q[i], dt);
+          al[m] = sh.rho[j] * dt;
+          for (int i = 0; i < d; ++i) q[i] = fmaf(-al[m], sh.yk[j][i], q[i]);
+        }
+        if (nmem > 0) {
+          const int j = (head - 1 + ASC_MEM) % ASC_MEM;
+          float yy = 0.f;
+          for (int i = 0; i < d; ++i) yy = fmaf(sh.yk[j][i], sh.yk[j][i], yy);
+          const float gamma = 1.f / (sh.rho[j] * yy);
+          for (int i = 0; i < d; ++i) q[i] *= gamma;
+        }
+        for (int m = nmem - 1; m >= 0; --m) {
+          const int j = (head - 1 - m + ASC_MEM) % ASC_MEM;
+          float dt = 0.f;
+          for (int i = 0; i < d; ++i) dt = fmaf(sh.yk[j][i], q[i], dt);
+          const float be = sh.rho[j] * dt;
+          for (int i = 0; i < d; ++i) q[i] = fmaf(al[m] - be, sh.sk[j][i], q[i]);
+        }
+        // p = -H grad h on the free set; fall back to steepest ascent when it is not an ascent direction of f
+        float slope = 0.f, gn = 0.f;
+        for (int i = 0; i < d; ++i) {
+          const float gi = sh.g[i];
+          const bool pinned = (sh.x[i] <= 0.f && gi < 0.f) || (sh.x[i] >= 1.f && gi > 0.f);
+          sh.p[i] = pinned ? 0.f : -q[i];
+          slope = fmaf(sh.p[i], gi, slope);
+          gn = fmaf(pinned ? 0.f : gi, gi, gn);
+        }
+        if (!(slope > 1e-12f * gn)) {
+          nmem = 0;  // drop the history, restart from a unit-length steepest-ascent step
+          head = 0;
+          const float sc = 1.f / fmaxf(sqrtf(gn), 1e-12f);
+          for (int i = 0; i < d; ++i) {
+            const float gi = sh.g[i];
+            const bool pinned = (sh.x[i] <= 0.f && gi < 0.f) || (sh.x[i] >= 1.f && gi > 0.f);
+            sh.p[i] = pinned ? 0.f : sc * gi;
+          }
+        } else if (nmem == 0) {  // first step: unit length (scipy's L-BFGS-B starts with 1 / |g|)
+          const float sc = 1.f / fmaxf(sqrtf(gn), 1e-12f);
+          for (int i = 0; i < d; ++i) sh.p[i] *= sc;
+        }
+      }
+      sh.flag = flag;
+    }
+    __syncthreads();
+    if (sh.flag) break;
+    // backtracking along the projected path x(t) = clip(x + t p)
+    float t = 1.f;
+    bool accepted = false;
+    for (int ls = 0; ls < 20; ++ls) {
+      if (tid < d) sh.xt[tid] = fminf(fmaxf(fmaf(t, sh.p[tid], sh.x[tid]), 0.f), 1.f);
+      __syncthreads();
+      asc_value_grad(a, s, sh.xt, sx, sxs, coef, coefk, sh.red, &sh.ft, sh.gt);
+      if (tid == 0) {
+        float lin = 0.f;
+        for (int i = 0; i < d; ++i) lin = fmaf(sh.g[i], sh.xt[i] - sh.x[i], lin);
+        sh.flag = (sh.ft >= sh.f + 1e-4f * lin && lin > 0.f) ? 1 : 0;
+      }
+      __syncthreads();
+      if (sh.flag) { accepted = true; break; }
+      __syncthreads();
+      t *= 0.5f;
+    }
+    if (!accepted) break;  // no progress along the direction: stop at the current point
+    if (tid == 0) {
+      float sy = 0.f, yy = 0.f;
+      const int j = head;
+      for (int i = 0; i < d; ++i) {
+        const float si = sh.xt[i] - sh.x[i];
+        const float yi = -(sh.gt[i] - sh.g[i]);  // gradient difference of h = -f
+        sh.sk[j][i] = si;
+        sh.yk[j][i] = yi;
+        sy = fmaf(si, yi, sy);
+        yy = fmaf(yi, yi, yy);
+      }
+      if (sy > 1e-10f * yy && yy > 0.f) {
+        sh.rho[j] = 1.f / sy;
+        head = (head + 1) % ASC_MEM;
+        nmem = min(nmem + 1, ASC_MEM);
+      }
+      const float df = sh.ft - sh.f;
+      sh.flag = (df <= ftol * fmaxf(fmaxf(fabsf(sh.f), fabsf(sh.ft)), 1.f)) ? 1 : 0;
+      for (int i = 0; i < d; ++i) {
+        sh.x[i] = sh.xt[i];
+        sh.g[i] = sh.gt[i];
+      }
+      sh.f = sh.ft;
+    }
+    __syncthreads();
+    if (sh.flag) { ++it; break; }
+  }
+  if (tid < d) xout[p * d + tid] = sh.x[tid];
+  if (tid == 0) {
+    fout[p] = sh.f;
+    if (iters) iters[p] = it;
+  }
+}
+
 }  // namespace psbax

@@ -121,15 +121,19 @@ __device__ __forceinline__ void epilogue_tile(const KArgs& a, const float* sOut,
   if constexpr (EPI == EPI_VALUES) {
     if (a.rowsq != nullptr) {  // sum of squares over this chunk's samples, thread <-> row, ascending s
       const int ns = min(TN, a.lay.S - s0);
+      const int grp = a.rowsq_group > 0 ? a.rowsq_group : TN;
       for (int r = tid; r < TM; r += NW * 32) {
         const long long row = (long long)row0 + r;
         if (row >= N) break;
-        float acc = 0.f;
-        for (int sl = 0; sl < ns; ++sl) {
-          const float y = fmaf(sOut[sl * OUT_LD + r], a.ystd, a.c0);
-          acc = fmaf(y, y, acc);
+        for (int g0 = 0; g0 < ns; g0 += grp) {
+          float acc = 0.f;
+          const int g1 = min(ns, g0 + grp);
+          for (int sl = g0; sl < g1; ++sl) {
+            const float y = fmaf(sOut[sl * OUT_LD + r], a.ystd, a.c0);
+            acc = fmaf(y, y, acc);
+          }
+          a.rowsq[(long long)((s0 + g0) / grp) * N + row] = acc;
         }
-        a.rowsq[(long long)(s0 / TN) * N + row] = acc;
       }
       return;
     }

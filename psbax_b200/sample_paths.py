@@ -193,6 +193,18 @@ class SamplePathBatch:
                                                  self._stream()), "psbax_eval_sumsq")
         return out
 
+    def sumsq_groups(self, X, group: int) -> torch.Tensor:
+        """``sum_{s in group g} f_s(X[i])**2``: [ceil(S / group), N] float32 on the GPU, one launch
+        (``psbax_eval_sumsq_groups``; ``group`` divides 64)."""
+        X = self._x(X)
+        N = X.shape[0]
+        with torch.cuda.device(self.device):
+            out = torch.empty((self.S + group - 1) // group, N, dtype=F32, device=self.device)
+            _lib.check(self.lib.psbax_eval_sumsq_groups(C.byref(self._struct), self._pack.data_ptr(), X.data_ptr(), N,
+                                                        group, out.data_ptr(), self._stream()),
+                       "psbax_eval_sumsq_groups")
+        return out
+
     def levelset(self, X, threshold: float, want_mask: bool = True, row_offset: int = 0,
                  want_pooled: bool = False, mesh=None, N: Optional[int] = None) -> LevelSetResult:
         """Fused evaluation + ``fx > threshold`` for all S paths.
@@ -342,6 +354,29 @@ class SamplePathBatch:
                                                 X.data_ptr(), N, _ptr(si), val.data_ptr(),
                                                 g.data_ptr(), self._stream()), "psbax_eval_grad")
         return val, g
+
+    def ascend(self, X0, sample_idx=None, maxiter: int = 100, pgtol: Optional[float] = None,
+               ftol: float = 2e-7) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """P independent box-constrained ascents on [0, 1]^d in one launch (``psbax_ascend``): ascent i
+        maximises path ``sample_idx[i]`` from ``X0[i]``.  Returns (x [P, d], f(x) [P], iterations [P])."""
+        if self.input_transform is not None:
+            raise PsbaxError("ascent through an input transform is not implemented")
+        X0 = self._x(X0)
+        P = X0.shape[0]
+        with torch.cuda.device(self.device):
+            si = None
+            if sample_idx is not None:
+                si = torch.as_tensor(sample_idx).to(self.device, torch.int32).contiguous().reshape(-1)
+                if si.numel() != P:
+                    raise PsbaxError("sample_idx must have one entry per row of X0")
+            x = torch.empty(P, self.d, dtype=F32, device=self.device)
+            f = torch.empty(P, dtype=F32, device=self.device)
+            it = torch.empty(P, dtype=torch.int32, device=self.device)
+            pg = 1e-5 * abs(self.y_std) if pgtol is None else float(pgtol)
+            _lib.check(self.lib.psbax_ascend(C.byref(self._struct), self._pack.data_ptr(), X0.data_ptr(), P, _ptr(si),
+                                             int(maxiter), pg, float(ftol), x.data_ptr(), f.data_ptr(), it.data_ptr(),
+                                             self._stream()), "psbax_ascend")
+        return x, f, it
 
     def subset_select(self, X, etas, k: int, nonneg: bool = False) -> torch.Tensor:
         """DiscoBAX greedy subset per sample (``src/algorithms/discobax.py:37-56``): [S, k] indices."""
@@ -555,6 +590,63 @@ def posterior_variance_params(model, pending: Optional[torch.Tensor] = None, jit
     S = X.shape[0]
     return dict(omega=torch.zeros(1, 0, d), bias=torch.zeros(1, 0), W=torch.zeros(S, 0), kernel=model.kernel,
                 Xtrain=X / ls, inv_ls=1.0 / ls, V=alpha * Linv, mean_const=0.0, y_mean=0.0, y_std=1.0)
+
+
+def fantasy_variance_params(model, path_xs, pending: Optional[torch.Tensor] = None, jitter: float = 1e-8,
+                            group: int = 16, device=None):
+    """Pseudo-paths for the posterior variance of the current model AND of one fantasy model per
+    execution path, over one candidate stream (SURVEY.md section 8, row f3;
+    ``src/acquisition_functions/bax_acquisition.py:87-122, 177-203``).
+
+    Base system: Z = [X; pending], K0 = k(Z, Z) + diag(sigma^2 .. | jitter ..) = L0 L0^T.  The fantasy of
+    path s (rows P_s, observed with the likelihood noise) has the block Cholesky factor
+    [[L0, 0], [B_s, L_s]],  B_s = k(P_s, Z) L0^-T,  L_s L_s^T = k(P_s, P_s) + sigma^2 I - B_s B_s^T, whose
+    inverse only ADDS the rows [-L_s^-1 B_s L0^-1, L_s^-1] to L0^-1.  So with the training set
+    [Z; P_1; ..; P_S] the pseudo-paths are: the n0 base rows (group-padded), then per path its k_s rows
+    (group-padded), and
+
+        var_0(x) = alpha - sum_{base groups} sumsq_g(x),     var_s(x) = var_0(x) - sum_{groups of s} sumsq_g(x).
+
+    Returns (SamplePathBatch kwargs, number of base groups, [groups per path])."""
+    dev = torch.device(device) if device is not None else default_device()
+    X, y, ls, alpha, noise, mu, y_mean, y_std = _model_state(model, dev)
+    from .models.gp import kernel_profile
+
+    def kmat(A, B):
+        a, b = A / ls, B / ls
+        return alpha * kernel_profile(((a[:, None, :] - b[None, :, :]) ** 2).sum(-1), model.kernel)
+
+    d = X.shape[1]
+    Z, diag = X, torch.full((X.shape[0],), float(noise), dtype=F64, device=dev)
+    if pending is not None and pending.numel() > 0:
+        P = pending.reshape(-1, d).to(dev, F64)
+        Z = torch.cat([Z, P])
+        diag = torch.cat([diag, torch.full((P.shape[0],), float(jitter) * float(alpha), dtype=F64, device=dev)])
+    n0 = Z.shape[0]
+    L0 = torch.linalg.cholesky(kmat(Z, Z) + torch.diag(diag))
+    L0inv = torch.linalg.solve_triangular(L0, torch.eye(n0, dtype=F64, device=dev), upper=False)
+    paths = [torch.as_tensor(p).reshape(-1, d).to(dev, F64) for p in path_xs]
+    pad = lambda k: ((k + group - 1) // group) * group  # noqa: E731
+    g0 = pad(n0) // group
+    gs = [pad(p.shape[0]) // group for p in paths]
+    n_total = n0 + sum(p.shape[0] for p in paths)
+    V = torch.zeros((g0 + sum(gs)) * group, n_total, dtype=F64, device=dev)
+    V[:n0, :n0] = L0inv
+    row, col = g0 * group, n0
+    for p, g in zip(paths, gs):
+        k = p.shape[0]
+        B = kmat(p, Z) @ L0inv.T
+        Cs = kmat(p, p) + float(noise) * torch.eye(k, dtype=F64, device=dev) - B @ B.T
+        Ls = torch.linalg.cholesky(0.5 * (Cs + Cs.T))
+        Lsinv = torch.linalg.solve_triangular(Ls, torch.eye(k, dtype=F64, device=dev), upper=False)
+        V[row:row + k, :n0] = -Lsinv @ B @ L0inv
+        V[row:row + k, col:col + k] = Lsinv
+        row, col = row + g * group, col + k
+    Xall = torch.cat([Z] + paths)
+    S = V.shape[0]
+    params = dict(omega=torch.zeros(1, 0, d), bias=torch.zeros(1, 0), W=torch.zeros(S, 0), kernel=model.kernel,
+                  Xtrain=Xall / ls, inv_ls=1.0 / ls, V=alpha * V, mean_const=0.0, y_mean=0.0, y_std=1.0)
+    return params, g0, gs
 
 
 def posterior_variance(model, Xq, pending: Optional[torch.Tensor] = None, device=None,

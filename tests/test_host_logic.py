@@ -3,6 +3,7 @@ callables (checked against the golden vectors the reference's own classes produc
 stand-in, the entropy pick, parameter draws (run on the CPU in float64 and evaluated by the
 oracle), and the missing-library failure mode."""
 import math
+import os
 import types
 
 import numpy as np
@@ -279,3 +280,66 @@ def test_posterior_variance_pseudo_paths_on_cpu():
                 ref.append(cov[0, 0] - cov[0, 1:] @ torch.linalg.solve(cov[1:, 1:], cov[1:, 0]))
             ref = torch.stack(ref)
         assert (var - ref).abs().max() <= 1e-6 * float(ref.max()) + 1e-9
+
+
+def test_fantasy_pseudo_paths_give_the_oracle_eig_on_cpu():
+    """Row f3: the block-Cholesky pseudo-paths of ``fantasy_variance_params`` (current model + one fantasy
+    model per execution path, one candidate stream) reproduce the oracle's restatement of
+    ``BAXAcquisitionFunction.forward`` (``bax_acquisition.py:87-122, 156-174``) in float64, with and without
+    pending rows, and the product's plain-torch ``forward`` equals the oracle too."""
+    from psbax_b200.acquisition_functions import BAXAcquisitionFunction
+    from psbax_b200.algorithms import TopK
+    from psbax_b200.sample_paths import fantasy_variance_params
+
+    gp = make_gp(14, 3, noise=1e-3, seed=6)
+    model = SingleTaskGP(gp.train_X, gp.train_Y, kernel=gp.kernel, lengthscale=gp.lengthscale,
+                         outputscale=gp.outputscale, noise=gp.noise, mean_const=gp.mean_const)
+    g = torch.Generator().manual_seed(2)
+    Xq = torch.rand(40, 3, dtype=torch.float64, generator=g)
+    paths = [(torch.rand(k, 3, dtype=torch.float64, generator=g), torch.randn(k, dtype=torch.float64, generator=g))
+             for k in (4, 4, 7, 1)]
+    paths[1] = (torch.cat([paths[1][0][:3], gp.train_X[:1]]), paths[1][1])  # a path row that duplicates a training row
+    alpha = float(model.covar_module.outputscale)
+    group = 4
+    for pending in (None, Xq[:2]):
+        ref = O.bax_eig(gp, paths, Xq[2:, None, :], pending)
+        kw, g0, gs = fantasy_variance_params(model, [p for p, _ in paths], pending=pending, group=group, device="cpu")
+        p = O.PathParams(omega=kw["omega"], bias=kw["bias"], W=kw["W"], kernel=kw["kernel"], Xtrain=kw["Xtrain"],
+                         inv_ls=kw["inv_ls"], V=kw["V"], mean_const=0.0, y_mean=0.0, y_std=1.0)
+        sq = (O.eval_paths(p, Xq[2:]) ** 2).T.reshape(g0 + sum(gs), group, -1).sum(1)  # [groups, N]
+        var0 = alpha - sq[:g0].sum(0)
+        eig, a = 0.5 * torch.log(var0), g0
+        for gk in gs:
+            eig = eig - 0.5 * torch.log(var0 - sq[a:a + gk].sum(0)) / len(gs)
+            a += gk
+        if pending is not None:  # x-independent terms: H_0(P) - mean_s H_s(P)
+            h = lambda m: 0.5 * torch.logdet(O.gp_posterior(m, pending)[1])  # noqa: E731
+            eig = eig + h(gp) - torch.stack([h(O.condition_on_observations(gp, px, py)) for px, py in paths]).mean()
+        assert (eig - ref).abs().max() <= 1e-7
+        # the host class's float64 forward (fantasy models by fit_with_old_model)
+        acq = BAXAcquisitionFunction(model, TopK({"x_path": Xq.numpy(), "k": 4}), exe_paths=len(paths))
+        acq.comb_model_list = [acq.fit_with_old_model(px, py) for px, py in paths]
+        acq.set_X_pending(pending)
+        assert (acq(Xq[2:, None, :]) - ref).abs().max() <= 1e-8
+
+
+def test_results_layout_round_trip(tmp_path):
+    """Row f4: the savetxt layout of src/one_trial.py:344-372 and its restart read-back (:69-113)."""
+    from psbax_b200.results import load_trial, save_trial
+
+    folder = str(tmp_path) + "/results/rosenbrock_3/ps_1/"
+    inputs = torch.rand(11, 3, dtype=torch.float64)
+    obj = torch.rand(11, dtype=torch.float64)
+    runtimes = [0.5, 0.25, 0.125]
+    metrics = [np.array([0.1]), np.array([0.2]), np.array([0.3]), np.array([0.4])]
+    save_trial(folder, 7, inputs, obj, runtimes, metrics)
+    for rel in ("inputs/inputs_7.txt", "obj_vals/obj_vals_7.txt", "runtimes/runtimes_7.txt", "performance_metrics_7.txt"):
+        assert os.path.exists(folder + rel)
+    assert np.loadtxt(folder + "inputs/inputs_7.txt").shape == (11, 3)
+    X, Y, rt, pm, it = load_trial(folder, 7)
+    assert torch.equal(X, inputs) and torch.equal(Y, obj) and rt == runtimes and it == 3
+    assert len(pm) == 4 and all(v.shape == (1,) for v in pm) and float(pm[2][0]) == 0.3
+    save_trial(folder, 8, inputs, obj, runtimes, [np.array([0.1, 1.0]), np.array([0.2, 2.0])])
+    assert load_trial(folder, 8)[3][1].tolist() == [0.2, 2.0]
+    with pytest.raises(OSError):
+        load_trial(folder, 9)
