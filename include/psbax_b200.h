@@ -208,6 +208,25 @@ int psbax_subset_select(const float* fx, int64_t ld_fx, const float* etas, int64
 int psbax_eval_grad(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
                     const int32_t* sample_idx, float* val, float* grad, void* stream);
 
+/* The feed-forward embedding of the deep-kernel GP (FFNN, src/models/deep_kernel_gp.py:18-84; the input
+ * transform of the DKGP / LinearKernel sample paths, src/utils.py:186-206): out[i, :] = net(X[i, :]) in
+ * fp32, Linear + activation layers with no activation after the last one.  W[l] is [width[l], width[l+1]]
+ * (the TRANSPOSE of torch.nn.Linear.weight, row-major), b[l] is [width[l+1]]; all DEVICE pointers.
+ * 1 <= n_layers <= PSBAX_MLP_MAX_LAYERS, every width <= 256. */
+#define PSBAX_MLP_MAX_LAYERS 8
+enum { PSBAX_ACT_RELU = 0, PSBAX_ACT_LEAKY_RELU = 1, PSBAX_ACT_SWISH = 2, PSBAX_ACT_SIGMOID = 3, PSBAX_ACT_TANH = 4 };
+typedef struct psbax_mlp {
+  int32_t n_layers;
+  int32_t activation;     /* PSBAX_ACT_* */
+  int32_t width[PSBAX_MLP_MAX_LAYERS + 1];
+  int32_t reserved;
+  const float* W[PSBAX_MLP_MAX_LAYERS];
+  const float* b[PSBAX_MLP_MAX_LAYERS];
+  float negative_slope;   /* leaky_relu (torch default 0.01) */
+  float reserved_f;
+} psbax_mlp_t;
+int psbax_mlp_forward(const psbax_mlp_t* mlp, const float* X, int64_t N, float* out, void* stream);
+
 /* Batched multi-start ascent: P independent box-constrained ascents on [0, 1]^d, ascent i maximising
  * sample path sample_idx[i] from the start X0[i, :], all inside ONE launch (one CTA per ascent; projected
  * L-BFGS with 8 curvature pairs and Armijo backtracking, value + gradient as psbax_eval_grad).  Replaces the

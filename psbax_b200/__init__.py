@@ -6,7 +6,7 @@ on top of the CUDA library ``libpsbax_b200.so`` (C ABI: ``include/psbax_b200.h``
 """
 from ._lib import PsbaxError  # noqa: F401
 from .sample_paths import (  # noqa: F401
-    LevelSetResult, SamplePath, SamplePathBatch, draw_dkgp_linear_paths, draw_matheron_paths,
+    LevelSetResult, MultiOutputSamplePathBatch, SamplePath, SamplePathBatch, draw_dkgp_linear_paths, draw_matheron_paths,
     draw_reference_paths, posterior_mean_path,
 )
 

@@ -20,7 +20,7 @@ ENGINE_IDS = {"auto": 0, "simt": 1, "tensor": 2, "tensor_bf16": 3, "tensor_proj"
 EXPORTS = [
     "psbax_version", "psbax_last_error", "psbax_debug_trace_buffer", "psbax_device_sms", "psbax_pack_bytes", "psbax_pack",
     "psbax_workspace_bytes", "psbax_eval_values", "psbax_sumsq_scratch_bytes", "psbax_eval_sumsq", "psbax_eval_sumsq_groups", "psbax_eval_levelset", "psbax_eval_levelset_ex", "psbax_eval_topk",
-    "psbax_topk_merge", "psbax_subset_select", "psbax_eval_grad", "psbax_ascend",
+    "psbax_topk_merge", "psbax_subset_select", "psbax_eval_grad", "psbax_ascend", "psbax_mlp_forward",
 ]
 
 
@@ -45,6 +45,18 @@ class MeshStruct(C.Structure):
     """``psbax_mesh_t``."""
 
     _fields_ = [("d", C.c_int32), ("reserved", C.c_int32), ("len", C.c_int64 * 4), ("axis", C.c_void_p * 4)]
+
+
+ACTIVATION_IDS = {"relu": 0, "leaky_relu": 1, "swish": 2, "sigmoid": 3, "tanh": 4}
+MLP_MAX_LAYERS = 8
+
+
+class MlpStruct(C.Structure):
+    """``psbax_mlp_t``."""
+
+    _fields_ = [("n_layers", C.c_int32), ("activation", C.c_int32), ("width", C.c_int32 * (MLP_MAX_LAYERS + 1)),
+                ("reserved", C.c_int32), ("W", C.c_void_p * MLP_MAX_LAYERS), ("b", C.c_void_p * MLP_MAX_LAYERS),
+                ("negative_slope", C.c_float), ("reserved_f", C.c_float)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -73,6 +85,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.psbax_subset_select.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp]
     lib.psbax_eval_grad.argtypes = [P, vp, vp, i64, vp, vp, vp, vp]
     lib.psbax_ascend.argtypes = [P, vp, vp, i64, vp, i32, f32, f32, vp, vp, vp, vp]
+    lib.psbax_mlp_forward.argtypes = [C.POINTER(MlpStruct), vp, i64, vp, vp]
     for name in EXPORTS:
         getattr(lib, name).restype = C.c_int
 

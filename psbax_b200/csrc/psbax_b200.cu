@@ -7,6 +7,7 @@
 #define PSBAX_TU_API 1
 #include "sp_common.cuh"
 #include "sp_extra.cuh"
+#include "sp_mlp.cuh"
 #include "sp_host_kernels.cuh"
 #include "sp_simt.cuh"
 #include "sp_tensor.cuh"
@@ -545,6 +546,39 @@ int psbax_ascend(const psbax_paths_t* paths, const void* pack, const float* X0, 
     CUDA_TRY(cudaFuncSetAttribute(k_ascend, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   k_ascend<<<(unsigned)P, 128, smem, st>>>(pr.a, sample_idx, x_out, f_out, iters, maxiter, pgtol, ftol);
+  CUDA_TRY(cudaGetLastError());
+  return PSBAX_OK;
+}
+
+int psbax_mlp_forward(const psbax_mlp_t* mlp, const float* X, int64_t N, float* out, void* stream) {
+  if (!mlp || !X || !out) return fail(PSBAX_E_INVALID, "mlp / X / out is NULL");
+  if (N < 1) return fail(PSBAX_E_INVALID, "N must be >= 1");
+  if (mlp->n_layers < 1 || mlp->n_layers > PSBAX_MLP_MAX_LAYERS)
+    return fail(PSBAX_E_INVALID, "n_layers=%d outside [1,%d]", mlp->n_layers, PSBAX_MLP_MAX_LAYERS);
+  if (mlp->activation < PSBAX_ACT_RELU || mlp->activation > PSBAX_ACT_TANH)
+    return fail(PSBAX_E_UNSUPPORTED, "activation id %d", mlp->activation);
+  MlpArgs a{};
+  a.n_layers = mlp->n_layers;
+  a.activation = mlp->activation;
+  a.slope = mlp->negative_slope;
+  a.X = X;
+  a.out = out;
+  a.N = N;
+  for (int l = 0; l <= mlp->n_layers; ++l) {
+    if (mlp->width[l] < 1 || mlp->width[l] > MLP_MAXW)
+      return fail(PSBAX_E_UNSUPPORTED, "layer width %d outside [1,%d]", mlp->width[l], MLP_MAXW);
+    a.width[l] = mlp->width[l];
+    if (mlp->width[l] > a.maxw) a.maxw = mlp->width[l];
+    if (l < mlp->n_layers) {
+      if (!mlp->W[l] || !mlp->b[l]) return fail(PSBAX_E_INVALID, "layer %d: W / b is NULL", l);
+      a.W[l] = mlp->W[l];
+      a.b[l] = mlp->b[l];
+    }
+  }
+  a.maxw = round_up(a.maxw, 4);
+  const size_t smem = ((size_t)2 * a.maxw * MLP_TM + MLP_WCHUNK) * sizeof(float);
+  CUDA_TRY(cudaFuncSetAttribute(k_mlp_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_mlp_forward<<<(unsigned)((N + MLP_TM - 1) / MLP_TM), MLP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(a);
   CUDA_TRY(cudaGetLastError());
   return PSBAX_OK;
 }

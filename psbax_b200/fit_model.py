@@ -6,7 +6,7 @@ import os
 
 import torch
 
-from .models import DKGP, SingleTaskGP
+from .models import DKGP, ModelListGP, SingleTaskGP
 
 
 def fit_model(inputs, outputs, model_type: str, **kwargs):
@@ -15,10 +15,11 @@ def fit_model(inputs, outputs, model_type: str, **kwargs):
     try:
         if model_type == "gp":
             kernel_type = kwargs.pop("kernel_type", None)
-            if outputs.shape[-1] != 1:
-                raise NotImplementedError("multi-output ModelListGP is not part of the accelerated path")
             # None -> botorch default Matern-5/2 ARD; "rbf"/"matern" -> plain non-ARD kernels (:29-36)
             kernel = {"rbf": "rbf", "matern": "matern52", None: "matern52"}[kernel_type]
+            if outputs.shape[-1] != 1:  # one model per output, each fitted, wrapped in a ModelListGP (:38-62)
+                return ModelListGP(*[SingleTaskGP(inputs, outputs[:, j:j + 1], kernel=kernel, ard=kernel_type is None).fit()
+                                     for j in range(outputs.shape[-1])])
             model = SingleTaskGP(inputs, outputs, kernel=kernel, ard=kernel_type is None)
             state = kwargs.pop("state_dict", None)
             if state is not None:  # fixed model without training (:50-54)

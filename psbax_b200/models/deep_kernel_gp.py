@@ -35,7 +35,10 @@ class DKGP:
     """``architecture`` = [d_in, ..., h, 1] as in the reference: the network maps d_in -> h and a
     GP with kernel  v * <e, e'>  (+ constant mean, Gaussian noise >= 1e-4) sits on the embedding."""
 
-    def __init__(self, train_X, train_Y, architecture, activation="leaky_relu"):
+    def __init__(self, train_X, train_Y, architecture, activation="leaky_relu", kernel="linear"):
+        """``kernel``: "linear" (what the reference hard-wires, ``deep_kernel_gp.py:112-116``) or
+        "rbf" / "matern12|32|52" on the embedding (the commented-out alternative there, which is what
+        the non-linear branch of ``get_function_samples``, ``src/utils.py:207-221``, serves)."""
         if len(architecture) <= 2:
             raise AttributeError("DKGP needs a hidden architecture (reference: deep_kernel_gp.py:100-101)")
         self.architecture = list(architecture)
@@ -43,8 +46,11 @@ class DKGP:
         self.feature_extractor = FFNN(architecture[:-1], activation)
         self.train_inputs = (train_X.to(DT),)
         self.train_targets = train_Y.to(DT).reshape(-1)
+        h = architecture[-2]
         self.covar_module = SimpleNamespace(
-            base_kernel=SimpleNamespace(variance=torch.tensor(1.0, dtype=DT), kind="linear"),
+            base_kernel=SimpleNamespace(variance=torch.tensor(1.0, dtype=DT), kind=kernel,
+                                        lengthscale=torch.ones(1, h, dtype=DT),
+                                        nu={"matern12": 0.5, "matern32": 1.5, "matern52": 2.5}.get(kernel)),
             outputscale=torch.tensor(1.0, dtype=DT))
         self.likelihood = SimpleNamespace(noise=torch.tensor([1e-2], dtype=DT))
         self.mean_module = SimpleNamespace(constant=torch.tensor(0.0, dtype=DT))
@@ -53,6 +59,19 @@ class DKGP:
         net = self.feature_extractor
         p = next(net.parameters())
         return net(X.to(p.device, p.dtype))
+
+    @property
+    def kernel(self) -> str:
+        return self.covar_module.base_kernel.kind
+
+    def _gram(self, E, v, ls=None):
+        """Kernel matrix of the embedded rows: v <e, e'> or v kappa(|e - e'| / ls)."""
+        if self.kernel == "linear":
+            return v * (E @ E.T)
+        from .gp import kernel_profile
+
+        a = E / (self.covar_module.base_kernel.lengthscale.reshape(-1).to(E) if ls is None else ls)
+        return v * kernel_profile(((a[:, None, :] - a[None, :, :]) ** 2).sum(-1), self.kernel)
 
     def weight_posterior(self, pending=None, jitter: float = 1e-8):
         """Weight-space posterior of the linear-kernel GP on the embedding (``src/utils.py:153-182``):
@@ -77,6 +96,8 @@ class DKGP:
         (what the exact GP with kernel v <e, e'> gives; no outcome transform, as in the reference)."""
         from .gp import Posterior
 
+        if self.kernel != "linear":
+            raise NotImplementedError("posterior() of the stand-in is the weight-space form of the linear kernel")
         mn, Sn = self.weight_posterior()
         with torch.no_grad():
             E = self.embedding(X.reshape(-1, X.shape[-1])).to(DT).reshape(*X.shape[:-1], -1)
@@ -89,16 +110,18 @@ class DKGP:
         X, Y = X.to(DT), Y.to(DT).reshape(-1)
         n = X.shape[0]
         raw = torch.zeros(3, dtype=DT, requires_grad=True)  # log v, log(noise - 1e-4), mu
+        h = self.architecture[-2]
+        raw_ls = torch.zeros(h, dtype=DT, requires_grad=self.kernel != "linear")  # log lengthscale (non-linear kernels)
         with torch.no_grad():
             raw[1] = math.log(1e-2)
-        params = list(self.feature_extractor.parameters()) + [raw]
+        params = list(self.feature_extractor.parameters()) + [raw] + ([raw_ls] if self.kernel != "linear" else [])
         opt = torch.optim.Adam(params, lr=lr)
         self.feature_extractor.train()
         for _ in range(num_iter):
             opt.zero_grad()
             E = self.feature_extractor(X)
             v, noise, mu = raw[0].exp(), raw[1].exp() + 1e-4, raw[2]
-            K = v * (E @ E.T) + noise * torch.eye(n, dtype=DT)
+            K = self._gram(E, v, raw_ls.exp()) + noise * torch.eye(n, dtype=DT)
             Lk = torch.linalg.cholesky(K)
             r = (Y - mu)[:, None]
             loss = 0.5 * (r * torch.cholesky_solve(r, Lk)).sum() + Lk.diagonal().log().sum()
@@ -107,6 +130,9 @@ class DKGP:
         self.feature_extractor.eval()
         with torch.no_grad():
             self.covar_module.base_kernel.variance = raw[0].exp().detach().clone()
+            if self.kernel != "linear":  # ScaleKernel(Matern / RBF): the scale is the outputscale
+                self.covar_module.outputscale = raw[0].exp().detach().clone()
+                self.covar_module.base_kernel.lengthscale = raw_ls.exp().detach().clone().reshape(1, -1)
             self.likelihood.noise = (raw[1].exp() + 1e-4).reshape(1).detach().clone()
             self.mean_module.constant = raw[2].detach().clone()
         return None

@@ -208,3 +208,36 @@ class SingleTaskGP:
                 self.mean_module.constant = raw[nls + 2].detach().clone()
         self.invalidate()
         return self
+
+
+class ModelListGP:
+    """Independent single-output GPs over the same inputs (botorch ``ModelListGP`` as
+    ``src/fit_model.py:59-62`` builds it): ``.models``, per-model ``train_inputs`` / ``train_targets``
+    lists, and a joint ``posterior`` whose mean is [..., q, m] (block-diagonal across outputs)."""
+
+    def __init__(self, *models):
+        if not models:
+            raise ValueError("ModelListGP needs at least one model")
+        self.models = list(models)
+
+    @property
+    def num_outputs(self) -> int:
+        return len(self.models)
+
+    @property
+    def train_inputs(self):
+        return [m.train_inputs for m in self.models]
+
+    @property
+    def train_targets(self):
+        return [m.train_targets for m in self.models]
+
+    def posterior(self, X: torch.Tensor):
+        posts = [m.posterior(X) for m in self.models]
+        covs = [p.covariance_matrix for p in posts]
+        q, m = covs[0].shape[-1], len(covs)
+        cov = covs[0].new_zeros(*covs[0].shape[:-2], m * q, m * q)  # outputs are independent: block diagonal
+        for j, c in enumerate(covs):
+            cov[..., j * q:(j + 1) * q, j * q:(j + 1) * q] = c
+        return SimpleNamespace(mean=torch.cat([p.mean for p in posts], dim=-1),  # [..., q, m]
+                               variance=torch.cat([p.variance for p in posts], dim=-1), covariance_matrix=cov)

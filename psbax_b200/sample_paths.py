@@ -85,6 +85,52 @@ def _stream_bounds(N: int, c: int):
     return bounds
 
 
+class DeviceFFNN:
+    """The deep-kernel GP's feed-forward embedding (``src/models/deep_kernel_gp.py:18-84``) as a CUDA
+    op: a float32 device COPY of the network's Linear layers (the caller's module is not moved or
+    modified) evaluated by ``psbax_mlp_forward`` — X [N, d_in] -> [N, h] float32 on the GPU."""
+
+    def __init__(self, net, device=None):
+        self.device = torch.device(device) if device is not None else default_device()
+        self.lib = _lib.load()
+        linears = [m for m in net.modules() if isinstance(m, torch.nn.Linear)]
+        if not 1 <= len(linears) <= _lib.MLP_MAX_LAYERS:
+            raise PsbaxError(f"embedding network with {len(linears)} Linear layers (supported: 1..{_lib.MLP_MAX_LAYERS})")
+        act = str(getattr(net, "activation", "leaky_relu")).lower()
+        if act not in _lib.ACTIVATION_IDS:
+            raise PsbaxError(f"activation {act!r} has no CUDA form")
+        with torch.no_grad():
+            self.W = [m.weight.detach().to(self.device, F32).T.contiguous() for m in linears]  # [in, out]
+            self.b = [(m.bias.detach() if m.bias is not None else torch.zeros(m.out_features)).to(self.device, F32).contiguous()
+                      for m in linears]
+        self.widths = [self.W[0].shape[0]] + [w.shape[1] for w in self.W]
+        if max(self.widths) > 256:
+            raise PsbaxError("embedding layers wider than 256 are not supported by psbax_mlp_forward")
+        self.h = self.widths[-1]
+        st = _lib.MlpStruct(n_layers=len(linears), activation=_lib.ACTIVATION_IDS[act], reserved=0,
+                            negative_slope=0.01, reserved_f=0.0)
+        for i, w in enumerate(self.widths):
+            st.width[i] = w
+        for i, (w, b) in enumerate(zip(self.W, self.b)):
+            st.W[i], st.b[i] = w.data_ptr(), b.data_ptr()
+        self._struct = st
+
+    def __call__(self, X) -> torch.Tensor:
+        X = torch.as_tensor(X)
+        X = X.reshape(-1, X.shape[-1])
+        if X.shape[1] != self.widths[0]:
+            raise PsbaxError(f"embedding expects {self.widths[0]} input columns, got {X.shape[1]}")
+        if X.device != self.device or X.dtype != F32 or not X.is_contiguous():
+            X = X.to(self.device, F32).contiguous()
+        with torch.cuda.device(self.device):
+            out = torch.empty(X.shape[0], self.h, dtype=F32, device=self.device)
+            if X.shape[0]:
+                _lib.check(self.lib.psbax_mlp_forward(C.byref(self._struct), X.data_ptr(), X.shape[0], out.data_ptr(),
+                                                      torch.cuda.current_stream(self.device).cuda_stream),
+                           "psbax_mlp_forward")
+        return out
+
+
 class SamplePathBatch:
     """S sample paths resident on one GPU."""
 
@@ -403,6 +449,56 @@ class SamplePathBatch:
         return (self.path(s) for s in range(self.S))
 
 
+class MultiOutputSamplePathBatch:
+    """S sample paths of an m-output ``ModelListGP`` (``src/utils.py:231-248``): one independent
+    ``SamplePathBatch`` per output model (its own basis, lengthscales and update weights), evaluated
+    over the same candidates and concatenated on the last dimension, as the reference's
+    ``aux_func`` does with the m ``get_gp_samples`` models."""
+
+    def __init__(self, batches):
+        self.batches = list(batches)
+        if len({b.S for b in self.batches}) != 1 or len({b.d for b in self.batches}) != 1:
+            raise PsbaxError("every output needs the same number of paths over the same input space")
+        self.S, self.d, self.m = self.batches[0].S, self.batches[0].d, len(self.batches)
+        self.device = self.batches[0].device
+
+    def values(self, X) -> torch.Tensor:
+        """[N, S, m] float32 on the GPU: m fused launches, one per output model."""
+        return torch.stack([b.values(X) for b in self.batches], dim=-1)
+
+    def output(self, j: int) -> SamplePathBatch:
+        return self.batches[j]
+
+    def path(self, s: int) -> "MultiOutputSamplePath":
+        return MultiOutputSamplePath(self, s)
+
+    def __len__(self) -> int:
+        return self.S
+
+    def __iter__(self):
+        return (self.path(s) for s in range(self.S))
+
+
+class MultiOutputSamplePath:
+    """One m-output sample with the calling convention of the ``GenericDeterministicModel`` the
+    reference returns for a ``ModelListGP`` (``src/utils.py:242-248``): X [b, 1, d] -> [b, 1, m]
+    (X [b, d] -> [b, m]); ``.posterior(X).mean`` gives the same tensor."""
+
+    def __init__(self, batch: MultiOutputSamplePathBatch, s: int):
+        self.batch, self.s = batch, s
+        self.paths = [b.path(s) for b in batch.batches]
+
+    def __call__(self, X) -> torch.Tensor:
+        X = torch.as_tensor(X)
+        out = torch.stack([p(X) for p in self.paths], dim=-1)  # [b, m]
+        return out.unsqueeze(1) if X.dim() == 3 else out
+
+    def posterior(self, X):
+        from types import SimpleNamespace
+
+        return SimpleNamespace(mean=self(X))
+
+
 class _PathValue(torch.autograd.Function):
     """f_s(X) with the CUDA gradient kernel as backward (LBFGSB needs d f / d x,
     ``src/algorithms/lbfgsb.py:29-39``)."""
@@ -675,23 +771,26 @@ def posterior_variance(model, Xq, pending: Optional[torch.Tensor] = None, device
     return (alpha - batch.sumsq(Xq)) * (float(y_std) ** 2)
 
 
+def _embedder(model, dev):
+    """The model's embedding as a GPU op that leaves the caller's network where it is."""
+    net = getattr(model, "feature_extractor", None)
+    if net is None:
+        return lambda X: torch.as_tensor(X).to(dev, F32)
+    return DeviceFFNN(net, dev)
+
+
 def _dkgp_posterior_variance(model, Xq, pending, dev, engine) -> torch.Tensor:
     """Deep-kernel GP (linear kernel on the embedding): var(x) = e(x)^T Sn e(x) = |Ls^T e(x)|^2 with
     Sn = Ls Ls^T the weight-space posterior covariance (conditioned on the pending rows): h linear-
     kernel pseudo-paths V = Ls^T over the embedded candidates — ``psbax_eval_sumsq`` gives the
     variance directly."""
-    net = model.feature_extractor.to(dev)
-    _, Sn = model.weight_posterior(pending.to(dev) if pending is not None else None)
+    _, Sn = model.weight_posterior(pending)
     Ls = torch.linalg.cholesky(Sn.to(dev))
     h = Ls.shape[0]
-
-    def embed(X):
-        return net(X.to(dev, next(net.parameters()).dtype)).to(F32)
-
     batch = SamplePathBatch(omega=torch.zeros(1, 0, h), bias=torch.zeros(1, 0), W=torch.zeros(h, 0), kernel="linear",
                             Xtrain=torch.eye(h, dtype=F64), inv_ls=torch.ones(h, dtype=F64), V=Ls.T.contiguous(),
                             mean_const=0.0, y_mean=0.0, y_std=1.0, device=dev, engine=engine or "auto",
-                            input_transform=embed)
+                            input_transform=_embedder(model, dev))
     return batch.sumsq(Xq)
 
 
@@ -703,7 +802,7 @@ def dkgp_linear_params(model, S: int, generator: Optional[torch.Generator] = Non
     transform."""
     dev = torch.device(device) if device is not None else default_device()
     with torch.no_grad():
-        E = model.embedding(model.train_inputs[0].to(dev)).to(F64)  # [n, h]
+        E = model.embedding(model.train_inputs[0]).to(dev, F64)  # [n, h] (float64, wherever the network lives)
         y = model.train_targets.to(dev, F64)
         h = E.shape[1]
         v = float(model.covar_module.base_kernel.variance)
@@ -720,15 +819,30 @@ def dkgp_linear_params(model, S: int, generator: Optional[torch.Generator] = Non
 
 
 def draw_dkgp_linear_paths(model, S: int, generator=None, device=None, engine: str = "auto") -> SamplePathBatch:
+    """The embedding of all N candidates runs in ``psbax_mlp_forward`` (float32, a device copy of the
+    network's weights: the caller's model stays on its device), fused evaluation + reduction after it."""
     dev = torch.device(device) if device is not None else default_device()
-    net = model.feature_extractor.to(dev) if getattr(model, "feature_extractor", None) is not None else None
-
-    def embed(X):
-        X = X.to(dev, next(net.parameters()).dtype) if net is not None else X.to(dev)
-        return (net(X) if net is not None else X).to(F32)
-
     return SamplePathBatch(**dkgp_linear_params(model, S, generator, dev), device=dev, engine=engine,
-                           input_transform=embed)
+                           input_transform=_embedder(model, dev))
+
+
+def draw_dkgp_rff_paths(model, S: int, L: int = 1000, generator=None, device=None, engine: str = "auto") -> SamplePathBatch:
+    """DKGP with an RBF / Matern kernel on the embedding (``src/utils.py:207-221``): the reference copies
+    the model, replaces its training inputs by their embedding and draws an RFF sample of that GP, then
+    evaluates it on ``embedding(X)``.  Same here with the Matheron form on the embedded training set;
+    the embedding is the batch's input transform (``psbax_mlp_forward``)."""
+    from .models.gp import SingleTaskGP
+
+    dev = torch.device(device) if device is not None else default_device()
+    with torch.no_grad():
+        E = model.embedding(model.train_inputs[0]).to("cpu", F64)
+    bk = model.covar_module.base_kernel
+    aux = SingleTaskGP(E, model.train_targets.to("cpu", F64), kernel=bk.kind, lengthscale=bk.lengthscale.to("cpu"),
+                       outputscale=float(model.covar_module.outputscale), noise=float(model.likelihood.noise.mean()),
+                       mean_const=float(model.mean_module.constant), standardize=False)  # targets standardized by fit_model
+    batch = SamplePathBatch(**matheron_params(aux, S, L, generator, dev), device=dev, engine=engine,
+                            input_transform=_embedder(model, dev))
+    return batch
 
 
 def draw_matheron_paths(model, S: int, L: int = 1000, generator=None, device=None,

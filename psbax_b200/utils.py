@@ -8,8 +8,8 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .sample_paths import (SamplePath, SamplePathBatch, draw_dkgp_linear_paths, draw_matheron_paths,
-                           draw_reference_paths, posterior_mean_path)
+from .sample_paths import (MultiOutputSamplePathBatch, SamplePath, SamplePathBatch, draw_dkgp_linear_paths,
+                           draw_dkgp_rff_paths, draw_matheron_paths, draw_reference_paths, posterior_mean_path)
 
 NUM_RFF_FEATURES = 1000  # hard-coded in the reference (src/utils.py:215,227,240)
 
@@ -26,8 +26,13 @@ def get_function_sample_batch(model, num_samples: int, **kwargs) -> SamplePathBa
     gen = kwargs.get("generator", None)
     device = kwargs.get("device", None)
     from .models.deep_kernel_gp import DKGP
-    if isinstance(model, DKGP):  # linear kernel on the embedding: exact weight-space draw (utils.py:186-206)
-        return draw_dkgp_linear_paths(model, num_samples, gen, device, kwargs.get("engine", "auto"))
+    from .models.gp import ModelListGP
+    if isinstance(model, DKGP):
+        if model.kernel == "linear":  # exact weight-space draw (utils.py:186-206)
+            return draw_dkgp_linear_paths(model, num_samples, gen, device, kwargs.get("engine", "auto"))
+        return draw_dkgp_rff_paths(model, num_samples, L, gen, device, kwargs.get("engine", "auto"))  # :207-221
+    if isinstance(model, ModelListGP):  # one batch of paths per output model (utils.py:231-248)
+        return MultiOutputSamplePathBatch([get_function_sample_batch(m, num_samples, **kwargs) for m in model.models])
     if sampler == "matheron":
         return draw_matheron_paths(model, num_samples, L, gen, device, kwargs.get("engine", "auto"))
     if sampler == "reference":
@@ -37,7 +42,8 @@ def get_function_sample_batch(model, num_samples: int, **kwargs) -> SamplePathBa
 
 def get_function_samples(model, **kwargs) -> SamplePath:
     """One posterior function sample as a callable — drop-in for
-    ``src/utils.py:185-250`` (SingleTaskGP branch): ``f(X[b, 1, d]) -> [b]``."""
+    ``src/utils.py:185-250``: ``f(X[b, 1, d]) -> [b]`` for a ``SingleTaskGP``, ``-> [b, 1, m]`` for a
+    ``ModelListGP`` of m outputs (``:231-248``)."""
     return get_function_sample_batch(model, 1, **kwargs).path(0)
 
 

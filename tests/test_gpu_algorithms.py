@@ -1,5 +1,6 @@
 """GPU tests of the reference-facing API: algorithm classes and the PS-BAX acquisition driving
 the fused kernels, against the oracle's restatement of the reference flow."""
+import math
 import types
 
 import numpy as np
@@ -474,3 +475,76 @@ def test_evolution_strategies_scores_populations_on_all_paths():
         assert abs(fbest - ep.y.max()) <= 1e-4 * float(scale[s])
     one, _ = EvolutionStrategies({"n_dim": d, "n_generation": 3, "n_population": 512, "seed": 1}).run_algorithm_on_f(paths.path(2))
     assert one.x.shape[1] == d
+
+
+def test_mlp_embedding_kernel_matches_torch():
+    """Row a2: the FFNN embedding (deep_kernel_gp.py:18-84) as psbax_mlp_forward, float32, against the
+    float64 torch network; ragged N, every activation, the GB1 architecture 80 -> 128 -> 64 -> 32."""
+    from psbax_b200.models import FFNN
+    from psbax_b200.sample_paths import DeviceFFNN
+
+    torch.manual_seed(0)
+    for arch, act, N in [([80, 128, 64, 32], "leaky_relu", 1000), ([12, 32, 16], "tanh", 77), ([5, 7], "relu", 3),
+                         ([33, 200, 9, 250, 31], "swish", 513), ([8, 16, 4], "sigmoid", 64)]:
+        net = FFNN(arch, act)
+        X = torch.randn(N, arch[0], dtype=torch.float64)
+        with torch.no_grad():
+            ref = net(X)
+        got = DeviceFFNN(net, "cuda")(X).double().cpu()
+        assert next(net.parameters()).device.type == "cpu"  # the caller's module is not moved
+        assert (got - ref).abs().max() <= 2e-5 * max(1.0, float(ref.abs().max())), (arch, act)
+
+
+def test_model_list_gp_paths_are_per_output_batches():
+    """Row a3: ModelListGP branch (src/utils.py:231-248): one batch of paths per output model, values
+    concatenated on the last dim; each output equals the oracle's evaluation of that output's parameters."""
+    from psbax_b200.models import ModelListGP
+    from psbax_b200.utils import get_function_sample_batch, get_function_samples
+
+    gps = [make_gp(9, 3, noise=1e-3, seed=1), make_gp(9, 3, kernel="rbf", noise=1e-2, seed=1)]
+    gps[1].train_Y = (gps[1].train_Y * 2.0 - 1.0)
+    gps[1].__post_init__()
+    model = ModelListGP(*[_model_from(g) for g in gps])
+    mb = get_function_sample_batch(model, 5, generator=torch.Generator(device="cuda").manual_seed(0), num_rff_features=128)
+    X = torch.rand(300, 3, dtype=torch.float64)
+    vals = mb.values(X)
+    assert vals.shape == (300, 5, 2)
+    for j in range(2):
+        p = _oracle_params(mb.output(j))
+        ref = O.eval_paths(p, X)
+        assert ((vals[..., j].double().cpu() - ref).abs().max(0).values <= 1e-4 * O.path_scale(p)).all()
+    f = mb.path(3)
+    out = f(X[:50].unsqueeze(1))
+    assert out.shape == (50, 1, 2)
+    assert (out[:, 0, :].cpu() - vals[:50, 3, :].double().cpu()).abs().max() <= 1e-4 * 4
+    assert f.posterior(X[:7].unsqueeze(1)).mean.shape == (7, 1, 2)
+    single = get_function_samples(model, generator=torch.Generator(device="cuda").manual_seed(0), num_rff_features=64)
+    assert single(X[:4].unsqueeze(1)).shape == (4, 1, 2)
+
+
+def test_dkgp_nonlinear_kernel_paths():
+    """Row a3: DKGP with a Matern kernel on the embedding (src/utils.py:207-221): RFF / Matheron paths of
+    the GP over the embedded training set, evaluated on embedding(X) — against the oracle fed the float64
+    torch embedding."""
+    from psbax_b200.models import DKGP
+    from psbax_b200.utils import get_function_sample_batch
+
+    torch.manual_seed(1)
+    X = torch.rand(30, 6, dtype=torch.float64)
+    y = torch.sin(3 * X.sum(-1))
+    y = (y - y.mean()) / y.std()
+    model = DKGP(X, y, [6, 16, 4, 1], kernel="matern52")
+    model.train_model(X, y, lr=1e-2, num_iter=20)
+    assert model.covar_module.base_kernel.lengthscale.shape == (1, 4)
+    paths = get_function_sample_batch(model, 4, generator=torch.Generator(device="cuda").manual_seed(2), num_rff_features=128)
+    Xq = torch.rand(200, 6, dtype=torch.float64)
+    with torch.no_grad():
+        Eq = model.embedding(Xq)
+        Et = model.embedding(X)
+    p = _oracle_params(paths)
+    ref = O.eval_paths(p, Eq)
+    got = paths.values(Xq).double().cpu()
+    assert ((got - ref).abs().max(0).values <= 2e-4 * O.path_scale(p)).all()  # fp32 embedding + fp32 evaluator
+    # the paths interpolate the (standardized) data up to the noise level
+    at_train = O.eval_paths(p, Et)
+    assert (at_train - y[:, None]).abs().max() <= 6 * math.sqrt(float(model.likelihood.noise))
