@@ -202,6 +202,16 @@ int psbax_topk_merge(const float* in_val, const int64_t* in_idx, int32_t lists, 
 int psbax_subset_select(const float* fx, int64_t ld_fx, const float* etas, int64_t N, int32_t B,
                         int32_t S, int32_t k, int32_t nonneg, int64_t* out_idx, void* stream);
 
+/* psbax_subset_select for the objective's other noise model and for per-sample noise
+ * (src/problems.py:146-163, get_noisy_f_lst): noise_mode PSBAX_NOISE_MULTIPLICATIVE scores
+ * values[b, i] = fx[i, s] * etas[b, i] with etas the 0 / 1 Bernoulli masks the objective draws;
+ * eta_stride_s != 0 gives every sample its own [B, N] noise matrix at etas + s * eta_stride_s (the
+ * reference draws a fresh mask per get_noisy_f_lst call, i.e. per sample path), 0 shares one. */
+enum { PSBAX_NOISE_ADDITIVE = 0, PSBAX_NOISE_MULTIPLICATIVE = 1 };
+int psbax_subset_select_ex(const float* fx, int64_t ld_fx, const float* etas, int64_t eta_stride_s, int64_t N,
+                           int32_t B, int32_t S, int32_t k, int32_t nonneg, int32_t noise_mode, int64_t* out_idx,
+                           void* stream);
+
 /* grad[i, :] = d f_{s_i}(X[i, :]) / dx and val[i] = f_{s_i}(X[i, :]) for a list of
  * (point, sample) pairs: what LBFGSB obtains through autograd
  * (src/algorithms/lbfgsb.py:29-39).  sample_idx is int32 [N] (NULL = sample 0). */

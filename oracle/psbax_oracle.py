@@ -492,15 +492,17 @@ def levelset_reduce(fx, threshold: float):
     return idx
 
 
-def subset_select_reduce(fx, etas, k: int, nonneg: bool = False):
+def subset_select_reduce(fx, etas, k: int, nonneg: bool = False, multiplicative: bool = False):
     """``SubsetSelect.run_algorithm_on_f`` (``src/algorithms/discobax.py:37-56``)
-    with additive noise (``src/problems.py:146-163``): values = fx + etas [B,N];
+    with the objective's noise model (``src/problems.py:146-163``): values = fx + etas [B,N], or, for
+    ``multiplicative``, values = fx * etas with etas the 0 / 1 Bernoulli masks (``:150-160``);
     first pick = argmax of the column means; then k-1 greedy picks maximising
     mean_b max(cur_max[b], values[b, j]) with already-chosen j scored 0.  The
     reference breaks exact ties at random (``discobax.py:79-83``); the oracle
     takes the smallest index."""
     fx = np.asarray(fx, dtype=np.float64).reshape(-1)
-    values = fx[None, :] + np.asarray(etas, dtype=np.float64)
+    etas = np.asarray(etas, dtype=np.float64)
+    values = fx[None, :] * etas if multiplicative else fx[None, :] + etas
     if nonneg:
         values = np.maximum(0.0, values)
     mean_values = values.mean(axis=0)

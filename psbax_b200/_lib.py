@@ -20,7 +20,7 @@ ENGINE_IDS = {"auto": 0, "simt": 1, "tensor": 2, "tensor_bf16": 3, "tensor_proj"
 EXPORTS = [
     "psbax_version", "psbax_last_error", "psbax_debug_trace_buffer", "psbax_device_sms", "psbax_pack_bytes", "psbax_pack",
     "psbax_workspace_bytes", "psbax_eval_values", "psbax_sumsq_scratch_bytes", "psbax_eval_sumsq", "psbax_eval_sumsq_groups", "psbax_eval_levelset", "psbax_eval_levelset_ex", "psbax_eval_topk",
-    "psbax_topk_merge", "psbax_subset_select", "psbax_eval_grad", "psbax_ascend", "psbax_mlp_forward",
+    "psbax_topk_merge", "psbax_subset_select", "psbax_subset_select_ex", "psbax_eval_grad", "psbax_ascend", "psbax_mlp_forward",
 ]
 
 
@@ -83,6 +83,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.psbax_eval_topk.argtypes = [P, vp, vp, i64, i64, i32, vp, vp, vp, sz, vp]
     lib.psbax_topk_merge.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.psbax_subset_select.argtypes = [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp]
+    lib.psbax_subset_select_ex.argtypes = [vp, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp]
     lib.psbax_eval_grad.argtypes = [P, vp, vp, i64, vp, vp, vp, vp]
     lib.psbax_ascend.argtypes = [P, vp, vp, i64, vp, i32, f32, f32, vp, vp, vp, vp]
     lib.psbax_mlp_forward.argtypes = [C.POINTER(MlpStruct), vp, i64, vp, vp]

@@ -113,7 +113,7 @@ class BAXAcquisitionFunction:
         except Exception as ex:
             if "engine needs" not in str(ex):
                 raise
-            batch = SamplePathBatch(**params, engine="auto")
+            batch = SamplePathBatch(**params, engine="simt")
         sq = batch.sumsq_groups(choices, group).double()  # [g0 + sum(gs), m]
         alpha = float(self.model.covar_module.outputscale)
         floor = 1e-6 * alpha

@@ -37,12 +37,25 @@ class EntropyAcquisitionFunction:
         from ..sample_paths import posterior_variance
 
         pend = self.X_pending
-        var = posterior_variance(self.model, choices, pending=pend).double().clamp_min(1e-300)
+        # alpha - sumsq is a float32 difference: floor it at its resolution (1e-6 of the prior variance)
+        # instead of letting rounding noise below zero turn into log(1e-300)
+        var = posterior_variance(self.model, choices, pending=pend).double().clamp_min(variance_floor(self.model))
         val = 0.5 * math.log(2 * math.pi) + 0.5 * torch.log(var)
         if pend is not None and pend.numel() > 0:
             covP = self.model.posterior(pend.reshape(1, -1, choices.shape[-1])).covariance_matrix[0]
             val = val + 0.5 * torch.logdet(covP).to(val.device)
         return val.to(torch.as_tensor(choices).device)
+
+
+def variance_floor(model) -> float:
+    """Smallest posterior variance (original units) the fused float32 path reports: 1e-6 of the prior
+    variance.  The true variance is >= ~noise / 2 at observed rows and ~jitter at pending rows; the
+    float32 difference alpha - |L^-1 k|^2 resolves neither below ~1e-6 alpha, so smaller (or negative)
+    results are rounding noise and all tie at the floor."""
+    if hasattr(model, "y_mean_std"):
+        alpha, y_std = float(model.covar_module.outputscale), float(model.y_mean_std()[1])
+        return 1e-6 * alpha * y_std * y_std
+    return 1e-12
 
 
 def _fusable(acq_function) -> bool:
@@ -78,7 +91,10 @@ def optimize_acqf_discrete(acq_function, q, choices, max_batch_size=100, unique=
         pend = torch.stack(picked)
         acq_function.set_X_pending(pend if base_pending is None else torch.cat([base_pending, pend]))
         if unique:
-            remaining = torch.cat([remaining[:j], remaining[j + 1:]])
+            if use_fused:  # every copy of the picked row goes: its conditional variance is now ~0 (float32 noise)
+                remaining = remaining[~(remaining == remaining[j]).all(dim=-1)]
+            else:
+                remaining = torch.cat([remaining[:j], remaining[j + 1:]])
         if remaining.shape[0] == 0:
             break
     acq_function.set_X_pending(base_pending)

@@ -72,19 +72,35 @@ class SubsetSelect(Algorithm):
         return self._greedy_host(torch.as_tensor(fx).detach().reshape(-1).numpy())
 
     def run_algorithm_on_batch(self, paths: SamplePathBatch):
-        """Values for all S paths in one launch, then the greedy for all S on the GPU."""
+        """Values for all S paths in one launch, then the greedy for all S on the GPU.
+
+        Additive noise: the objective's ``etas`` [B, N] serve every path.  Multiplicative noise
+        (``src/problems.py:150-160``): the objective draws a fresh Bernoulli mask in every
+        ``get_noisy_f_lst`` call, i.e. per path; the S masks are drawn here in path order through the
+        objective itself (``get_noisy_f_lst(ones)``: same RNG consumption as S reference calls) and the
+        greedy runs on ``fx * mask`` with one mask per path."""
         self.initialize()
-        if getattr(self.obj_func, "noise_type", "additive") != "additive":
-            raise NotImplementedError("GPU subset select implements the additive-noise objective")
+        noise_type = getattr(self.obj_func, "noise_type", "additive")
         X, etas = self._device_inputs(paths.device)
         nonneg = bool(getattr(self.obj_func, "nonneg", False))
-        idx = paths.subset_select(X, etas, self.params.k, nonneg).cpu().numpy()
-        fx_all = paths.values(X).double().cpu().numpy()  # exe_path.y / .values bookkeeping
+        fx_dev = paths.values(X)
+        fx_all = fx_dev.double().cpu().numpy()  # exe_path.y / .values bookkeeping
+        N = fx_all.shape[0]
+        if noise_type == "additive":
+            idx = paths.subset_select(X, etas, self.params.k, nonneg).cpu().numpy()
+            values = [None] * paths.S
+        elif noise_type == "multiplicative":
+            masks = np.stack([np.asarray(self.obj_func.get_noisy_f_lst(np.ones(N)), dtype=np.float64)
+                              for _ in range(paths.S)])  # [S, B, N] of 0 / 1
+            idx = paths.subset_select(X, torch.from_numpy(masks), self.params.k, nonneg, noise="multiplicative").cpu().numpy()
+            values = [np.maximum(0, fx_all[:, s] * masks[s]) if nonneg else fx_all[:, s] * masks[s] for s in range(paths.S)]
+        else:
+            raise NotImplementedError(f"noise_type {noise_type!r}")
         results = []
         for s in range(paths.S):
             self.initialize()
             fx = fx_all[:, s]
-            results.append(self._finish(idx[s], fx, self.obj_func.get_noisy_f_lst(fx)))
+            results.append(self._finish(idx[s], fx, values[s] if values[s] is not None else self.obj_func.get_noisy_f_lst(fx)))
         return results
 
     def get_values_and_selected_indices(self):

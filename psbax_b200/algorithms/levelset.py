@@ -63,19 +63,40 @@ class LevelSetEstimator(Algorithm):
             fx = np.asarray(f(self.params.x_set)).flatten()
         return self._from_values(fx)
 
-    def run_algorithm_on_batch(self, paths: SamplePathBatch, with_values: bool = True):
-        """One fused launch for all S paths -> [(exe_path, output)] in sample order."""
+    def run_algorithm_on_batch(self, paths: SamplePathBatch, with_values: bool = True, chunk_rows: int = 1 << 18):
+        """One fused launch for all S paths -> [(exe_path, output)] in sample order.
+
+        ``exe_path.y`` comes from the SAME batch and engine that decided membership: the values of the
+        union of the S super-level sets are evaluated once (row chunks of the union, all S paths per
+        launch) and every path gathers its own rows — no per-path repack / launch, and y > threshold
+        holds for every reported row up to the engine's rounding of one and the same number."""
         X = self.device_candidates(paths.device)
-        res = paths.levelset(X, self.params.threshold)
-        results = []
+        N = X.shape[0]
+        res = paths.levelset(X, self.params.threshold, want_mask=True, want_pooled=True)
+        idxs = [res.indices(s) for s in range(paths.S)]  # ascending row indices per path (or [arg max])
+        ys = [torch.full((i.numel(),), float("nan"), dtype=torch.float64, device=paths.device) for i in idxs]
+        if with_values:
+            shifts = torch.arange(32, device=paths.device, dtype=torch.int32)
+            pool = ((res.pooled.unsqueeze(1) >> shifts) & 1).bool().reshape(-1)[:N].clone()
+            empty = res.count == 0
+            if bool(empty.any()):
+                pool[res.argmax[empty]] = True
+            union = pool.nonzero().reshape(-1)
+            for rows in union.split(chunk_rows):
+                V = paths.values(X[rows]).double()  # [c, S]
+                lo, hi = rows[0], rows[-1]
+                for s, idx in enumerate(idxs):
+                    a, b = int(torch.searchsorted(idx, lo)), int(torch.searchsorted(idx, hi, right=True))
+                    if b > a:
+                        ys[s][a:b] = V[torch.searchsorted(rows, idx[a:b]), s]
+        sizes = [i.numel() for i in idxs]
+        idx_h = torch.cat(idxs).cpu().numpy()
+        y_h = torch.cat(ys).cpu().numpy()
+        results, o = [], 0
         for s in range(paths.S):
             self.initialize()
-            idx = res.indices(s)
-            if with_values:
-                y = paths.path(s)._one().values(X[idx])[:, 0].double().cpu().numpy()
-            else:
-                y = np.full(idx.numel(), np.nan)
-            results.append(self._finish(idx.cpu().numpy(), y))
+            results.append(self._finish(idx_h[o:o + sizes[s]], y_h[o:o + sizes[s]]))
+            o += sizes[s]
         return results
 
     def pooled_mask(self, paths: SamplePathBatch) -> torch.Tensor:

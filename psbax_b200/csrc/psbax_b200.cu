@@ -513,6 +513,32 @@ int psbax_subset_select(const float* fx, int64_t ld_fx, const float* etas, int64
   return PSBAX_OK;
 }
 
+int psbax_subset_select_ex(const float* fx, int64_t ld_fx, const float* etas, int64_t eta_stride_s, int64_t N,
+                           int32_t B, int32_t S, int32_t k, int32_t nonneg, int32_t noise_mode, int64_t* out_idx,
+                           void* stream) {
+  if (noise_mode == PSBAX_NOISE_ADDITIVE && eta_stride_s == 0)
+    return psbax_subset_select(fx, ld_fx, etas, N, B, S, k, nonneg, out_idx, stream);
+  if (noise_mode != PSBAX_NOISE_ADDITIVE && noise_mode != PSBAX_NOISE_MULTIPLICATIVE)
+    return fail(PSBAX_E_INVALID, "noise_mode=%d", noise_mode);
+  if (!fx || !etas || !out_idx) return fail(PSBAX_E_INVALID, "NULL buffer");
+  if (N < 1 || B < 1 || S < 1 || k < 1) return fail(PSBAX_E_INVALID, "N, B, S, k must be >= 1");
+  if (k > N) return fail(PSBAX_E_INVALID, "k=%d > N=%lld", k, (long long)N);
+  if (ld_fx < S) return fail(PSBAX_E_INVALID, "ld_fx < S");
+  if (N > 2147483647LL) return fail(PSBAX_E_UNSUPPORTED, "N exceeds 2^31");
+  if (eta_stride_s != 0 && eta_stride_s < (int64_t)B * N) return fail(PSBAX_E_INVALID, "eta_stride_s < B * N");
+  const size_t smem = ((size_t)B + k) * 4;
+  if (smem > 40 * 1024) return fail(PSBAX_E_UNSUPPORTED, "B=%d too large for shared memory", B);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long* oi = reinterpret_cast<long long*>(out_idx);
+  const bool mul = noise_mode == PSBAX_NOISE_MULTIPLICATIVE;
+  if (mul && nonneg) k_subset_select_general<true, true><<<S, 256, smem, st>>>(fx, ld_fx, etas, eta_stride_s, N, B, k, oi);
+  else if (mul) k_subset_select_general<true, false><<<S, 256, smem, st>>>(fx, ld_fx, etas, eta_stride_s, N, B, k, oi);
+  else if (nonneg) k_subset_select_general<false, true><<<S, 256, smem, st>>>(fx, ld_fx, etas, eta_stride_s, N, B, k, oi);
+  else k_subset_select_general<false, false><<<S, 256, smem, st>>>(fx, ld_fx, etas, eta_stride_s, N, B, k, oi);
+  CUDA_TRY(cudaGetLastError());
+  return PSBAX_OK;
+}
+
 int psbax_eval_grad(const psbax_paths_t* paths, const void* pack, const float* X, int64_t N,
                     const int32_t* sample_idx, float* val, float* grad, void* stream) {
   Prepared pr;

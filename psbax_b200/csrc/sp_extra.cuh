@@ -205,6 +205,77 @@ __global__ void __launch_bounds__(512) k_subset_select(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------
+// SubsetSelect, general noise model (src/problems.py:146-163, get_noisy_f_lst): one CTA per sample,
+//   values[b, j] = fx[j, s] + etas[b, j]   (MUL == false)   or   fx[j, s] * etas[b, j]   (MUL == true: the
+//   multiplicative model, etas = the Bernoulli masks the objective draws, 0 / 1),
+// optionally max(0, .), with one noise matrix for all samples (eta_stride_s == 0) or one per sample
+// (the reference draws a fresh mask in every get_noisy_f_lst call, i.e. per sample path).  Same
+// greedy, same tie rule (smaller index) as k_subset_select; the additive shared-noise case uses the
+// register-blocked kernel above.
+// ---------------------------------------------------------------------------------
+template <bool MUL, bool NONNEG>
+__global__ void __launch_bounds__(256) k_subset_select_general(const float* __restrict__ fx, long long ld_fx,
+                                                               const float* __restrict__ etas,
+                                                               long long eta_stride_s, long long N, int B, int k,
+                                                               long long* __restrict__ out_idx) {
+  extern __shared__ __align__(16) float smem[];
+  float* cur = smem;                                   // [B]
+  int* chosen = reinterpret_cast<int*>(cur + B);       // [k]
+  __shared__ float redv[8];
+  __shared__ int redi[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int s = blockIdx.x;
+  const float* __restrict__ E = etas + (long long)s * eta_stride_s;
+  const float invB = 1.0f / (float)B;
+  for (int b = tid; b < B; b += blockDim.x) cur[b] = -CUDART_INF_F;
+  __syncthreads();
+  for (int step = 0; step < k; ++step) {
+    float bv = -CUDART_INF_F;
+    int bi = 0x7fffffff;
+    for (long long j = tid; j < N; j += blockDim.x) {
+      const float f = __ldg(fx + j * ld_fx + s);
+      float acc = 0.f;
+      for (int b = 0; b < B; ++b) {  // ascending b: same rounding as the host loop
+        const float e = __ldg(E + (long long)b * N + j);
+        float v = MUL ? f * e : f + e;
+        if (NONNEG) v = fmaxf(v, 0.f);
+        acc += fmaxf(v, cur[b]);
+      }
+      float score = acc * invB;
+      for (int q = 0; q < step; ++q)
+        if (chosen[q] == (int)j) score = 0.f;
+      if (better(score, (int)j, bv, bi)) { bv = score; bi = (int)j; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { redv[warp] = bv; redi[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      float v = redv[0];
+      int i = redi[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+        if (better(redv[w], redi[w], v, i)) { v = redv[w]; i = redi[w]; }
+      chosen[step] = i;
+      out_idx[(long long)s * k + step] = i;
+    }
+    __syncthreads();
+    const int jp = chosen[step];
+    const float fp = __ldg(fx + (long long)jp * ld_fx + s);
+    for (int b = tid; b < B; b += blockDim.x) {
+      const float e = __ldg(E + (long long)b * N + jp);
+      float v = MUL ? fp * e : fp + e;
+      if (NONNEG) v = fmaxf(v, 0.f);
+      cur[b] = fmaxf(cur[b], v);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // Gradient of one sample path per point (LBFGSB, src/algorithms/lbfgsb.py:29-39).
 // One CTA (128 threads) per point: phase 1 stores coef_l = -w_l sin(arg_l) (and the
 // kernel-term coefficients) in shared memory and reduces the value; phase 2 thread

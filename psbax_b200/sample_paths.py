@@ -424,19 +424,26 @@ class SamplePathBatch:
                                              self._stream()), "psbax_ascend")
         return x, f, it
 
-    def subset_select(self, X, etas, k: int, nonneg: bool = False) -> torch.Tensor:
-        """DiscoBAX greedy subset per sample (``src/algorithms/discobax.py:37-56``): [S, k] indices."""
+    def subset_select(self, X, etas, k: int, nonneg: bool = False, noise: str = "additive") -> torch.Tensor:
+        """DiscoBAX greedy subset per sample (``src/algorithms/discobax.py:37-56``): [S, k] indices.
+        ``etas``: [B, N] (one noise matrix for all paths) or [S, B, N] (one per path); ``noise``:
+        "additive" (values = fx + etas) or "multiplicative" (values = fx * etas, etas the 0 / 1 masks of
+        ``src/problems.py:150-160``)."""
         fx = self.values(X)
         N = fx.shape[0]
         etas = torch.as_tensor(etas).to(self.device, F32).contiguous()
-        if etas.dim() != 2 or etas.shape[1] != N:
-            raise PsbaxError("etas must be [B, N]")
+        if etas.dim() not in (2, 3) or etas.shape[-1] != N or (etas.dim() == 3 and etas.shape[0] != self.S):
+            raise PsbaxError("etas must be [B, N] or [S, B, N]")
+        if noise not in ("additive", "multiplicative"):
+            raise PsbaxError(f"noise model {noise!r}")
+        B = etas.shape[-2]
         with torch.cuda.device(self.device):
             out = torch.empty(self.S, k, dtype=torch.int64, device=self.device)
-            _lib.check(self.lib.psbax_subset_select(fx.data_ptr(), self.S, etas.data_ptr(), N,
-                                                    etas.shape[0], self.S, k, int(bool(nonneg)),
-                                                    out.data_ptr(), self._stream()),
-                       "psbax_subset_select")
+            _lib.check(self.lib.psbax_subset_select_ex(fx.data_ptr(), self.S, etas.data_ptr(),
+                                                       B * N if etas.dim() == 3 else 0, N, B, self.S, k,
+                                                       int(bool(nonneg)), int(noise == "multiplicative"),
+                                                       out.data_ptr(), self._stream()),
+                       "psbax_subset_select_ex")
         return out
 
     def path(self, s: int) -> "SamplePath":
@@ -760,10 +767,10 @@ def posterior_variance(model, Xq, pending: Optional[torch.Tensor] = None, device
     if engine is None:
         try:
             batch = SamplePathBatch(**params, device=dev, engine="tensor")
-        except _lib.PsbaxError as ex:  # operands too large for the TF32 images
-            if "engine needs" not in str(ex):
+        except _lib.PsbaxError as ex:  # operands too large for the TF32 images: the FFMA engine (full fp32
+            if "engine needs" not in str(ex):  # products), never the BF16x3 split, for a difference that cancels
                 raise
-            batch = SamplePathBatch(**params, device=dev, engine="auto")
+            batch = SamplePathBatch(**params, device=dev, engine="simt")
     else:
         batch = SamplePathBatch(**params, device=dev, engine=engine)
     alpha = float(model.covar_module.outputscale)

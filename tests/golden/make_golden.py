@@ -17,7 +17,8 @@ reference's code, unmodified.
 ``SubsetSelect`` needs an objective exposing ``get_x()``, ``df.index`` and
 ``get_noisy_f_lst(fx)``; ``src/problems.py`` imports gpytorch at module level, so
 a stand-in with the additive-noise arithmetic of ``src/problems.py:146-163``
-(``values = fx + etas``; optional ``max(0, .)``) is used.
+(``values = fx + etas``; optional ``max(0, .)``) is used, plus one with the multiplicative arithmetic
+of ``:150-160`` (``values = fx * mask``) whose Bernoulli mask is drawn once and stored.
 """
 import os
 import sys
@@ -81,6 +82,24 @@ class _FakeDiscoObjective:
 
     def get_noisy_f_lst(self, fx):  # src/problems.py:146-163, additive branch
         values = fx.squeeze() + self.etas
+        if self.nonneg:
+            values = np.maximum(0, values)
+        return values
+
+
+class _FakeDiscoObjectiveMul(_FakeDiscoObjective):
+    """Multiplicative branch of ``get_noisy_f_lst`` (``src/problems.py:150-160``): values = fx * mask with
+    mask ~ Bernoulli(sigmoid(etas)).  The reference draws the mask from the global NumPy RNG in every
+    call; here it is drawn ONCE (seeded) and stored, so that the golden case is reproducible — the
+    greedy that consumes ``values`` is still the reference's."""
+
+    def __init__(self, x, etas, nonneg, seed):
+        super().__init__(x, etas, nonneg)
+        p = 1.0 / (1.0 + np.exp(-self.etas))
+        self.mask = np.random.default_rng(seed).binomial(1, p).astype(np.float64)
+
+    def get_noisy_f_lst(self, fx):
+        values = np.multiply(fx.squeeze(), self.mask)
         if self.nonneg:
             values = np.maximum(0, values)
         return values
@@ -163,6 +182,27 @@ def main():
                     pre + "values": np.asarray(exe_path.values)})
         case += 1
     out["n_ss"] = np.int64(case)
+
+    # ---- SubsetSelect with the multiplicative noise model (src/problems.py:150-160) --------
+    case = 0
+    for (N, d, B, k, nonneg) in [(80, 3, 9, 4, False), (150, 4, 16, 4, True)]:  # k small enough that no greedy step is an exact tie
+        A = rng.normal(size=(d, 16)) * 2.0
+        c = rng.uniform(0, 2 * np.pi, size=16)
+        w = rng.normal(size=16) * 0.5
+        x = rng.uniform(size=(N, d))
+        etas = rng.normal(size=(B, N))
+        f = smooth_fn(A, c, w)
+        obj = _FakeDiscoObjectiveMul(x, etas, nonneg, seed=100 + case)
+        algo = SubsetSelect({"k": k})
+        algo.set_obj_func(obj)
+        exe_path, indices = algo.run_algorithm_on_f(f(x).numpy())
+        pre = f"sm{case}_"
+        out.update({pre + "A": A, pre + "c": c, pre + "w": w, pre + "x": x, pre + "mask": obj.mask,
+                    pre + "k": np.int64(k), pre + "nonneg": np.bool_(nonneg),
+                    pre + "idxes": np.asarray(exe_path.idxes, dtype=np.int64),
+                    pre + "labels": np.asarray(indices), pre + "values": np.asarray(exe_path.values)})
+        case += 1
+    out["n_sm"] = np.int64(case)
 
     np.savez_compressed(OUT, **out)
     print("wrote", OUT, os.path.getsize(OUT), "bytes")

@@ -425,3 +425,32 @@ def test_randomised_shapes_all_engines():
             srt = -np.sort(-ref, axis=0)[:k].T  # [S, k]
             assert (np.abs(val - srt) <= tol[:, None]).all(), tag
             assert (np.abs(np.take_along_axis(ref.T, idx, 1) - val) <= tol[:, None]).all(), tag
+
+
+def test_subset_select_multiplicative_and_per_sample_noise():
+    """psbax_subset_select_ex: the multiplicative noise model (values = fx * mask, src/problems.py:150-160)
+    with one mask per sample path (the reference draws a fresh one per get_noisy_f_lst call), and additive
+    noise with per-sample matrices, against the oracle's greedy on the same values."""
+    for (S, N, B, k, nonneg, noise) in [(5, 300, 12, 5, False, "multiplicative"), (33, 130, 7, 4, True, "multiplicative"),
+                                        (4, 200, 9, 3, False, "additive")]:
+        p = random_params(S, 64, 5, 12, seed=S + 3)
+        X = candidates(N, 5)
+        g = torch.Generator().manual_seed(7)
+        if noise == "multiplicative":
+            etas = (torch.rand(S, B, N, generator=g) < 0.6).float()
+        else:
+            etas = 0.7 * torch.randn(S, B, N, generator=g)
+        batch = to_batch(p)
+        idx = batch.subset_select(X.cuda(), etas, k, nonneg, noise=noise).cpu().numpy()
+        shared = batch.subset_select(X.cuda(), etas[0], k, nonneg, noise=noise).cpu().numpy()
+        fx = batch.values(X.cuda()).double().cpu().numpy()
+        for s in range(S):
+            for got, e in ((idx[s], etas[s]), (shared[s], etas[0])):
+                oidx, values = O.subset_select_reduce(fx[:, s], e.double().numpy(), k, nonneg,
+                                                      multiplicative=noise == "multiplicative")
+                if got.tolist() == oidx:
+                    continue
+
+                def score(sel):
+                    return np.max(values[:, sel], axis=1).mean()
+                assert abs(score(got.tolist()) - score(oidx)) <= 1e-5 * max(1.0, abs(score(oidx)))

@@ -343,3 +343,25 @@ def test_results_layout_round_trip(tmp_path):
     assert load_trial(folder, 8)[3][1].tolist() == [0.2, 2.0]
     with pytest.raises(OSError):
         load_trial(folder, 9)
+
+
+def test_subset_select_class_multiplicative_golden(golden):
+    """Host greedy on the multiplicative noise model == the reference's class on the same values."""
+    for i in range(int(golden["n_sm"])):
+        pre = f"sm{i}_"
+        f = _fn(golden, pre)
+        x, mask, nonneg = golden[pre + "x"], golden[pre + "mask"], bool(golden[pre + "nonneg"])
+
+        class Obj(_Obj):
+            noise_type = "multiplicative"
+
+            def get_noisy_f_lst(self, fx):
+                v = np.multiply(np.asarray(fx).squeeze(), mask)
+                return np.maximum(0, v) if self.nonneg else v
+
+        algo = SubsetSelect({"k": int(golden[pre + "k"])})
+        algo.set_obj_func(Obj(x, mask, nonneg))
+        exe_path, labels = algo.run_algorithm_on_f(f(x).numpy())
+        assert exe_path.idxes == golden[pre + "idxes"].tolist()
+        assert list(labels) == golden[pre + "labels"].tolist()
+        np.testing.assert_allclose(exe_path.values, golden[pre + "values"], atol=1e-12)

@@ -136,3 +136,17 @@ def test_mesh_helpers_match_reference_layout():
     # 'ij' order: the first coordinate varies slowest (src/utils.py:273-286)
     assert torch.allclose(X[:4, 0], torch.zeros(4, dtype=torch.float64))
     assert torch.allclose(X[:4, 1], torch.linspace(0, 1, 4, dtype=torch.float64))
+
+
+def test_golden_subset_select_multiplicative(golden):
+    """The multiplicative noise model (src/problems.py:150-160) through the reference's own greedy."""
+    assert int(golden["n_sm"]) >= 2
+    for i in range(int(golden["n_sm"])):
+        pre = f"sm{i}_"
+        x = torch.from_numpy(golden[pre + "x"])
+        fx = (torch.cos(x @ torch.from_numpy(golden[pre + "A"]) + torch.from_numpy(golden[pre + "c"]))
+              @ torch.from_numpy(golden[pre + "w"])).numpy()
+        idxes, values = O.subset_select_reduce(fx, golden[pre + "mask"], int(golden[pre + "k"]),
+                                               bool(golden[pre + "nonneg"]), multiplicative=True)
+        assert idxes == golden[pre + "idxes"].tolist()
+        np.testing.assert_allclose(values, golden[pre + "values"], atol=1e-12)
