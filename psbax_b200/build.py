@@ -33,18 +33,23 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, trace: bool = False, variant: str = "",
+          defines=()) -> str:
     """trace=True builds libpsbax_b200_trace.so with the clock64 pipeline trace compiled in
-    (profiling aid; select it with PSBAX_LIB=<path>)."""
+    (profiling aid; select it with PSBAX_LIB=<path>).  variant="name" + defines=("-DX=1", ...) builds
+    libpsbax_b200_<name>.so for same-box A/B timing of an experiment."""
     out = OUT.replace(".so", "_trace.so") if trace else OUT
-    if not force and not trace and not _stale():
+    if variant:
+        out = OUT.replace(".so", f"_{variant}.so")
+    if not force and not trace and not variant and not _stale():
         return OUT
     # one object per translation unit, compiled in parallel, then one link
     from concurrent.futures import ThreadPoolExecutor
 
-    objdir = os.path.join(HERE, "build", "trace" if trace else "obj")
+    objdir = os.path.join(HERE, "build", variant or ("trace" if trace else "obj"))
     os.makedirs(objdir, exist_ok=True)
-    flags = NVCC_FLAGS + (["-DPSBAX_TC_TRACE=1"] if trace else []) + (["-Xptxas", "-v"] if verbose else [])
+    flags = (NVCC_FLAGS + (["-DPSBAX_TC_TRACE=1"] if trace else []) + list(defines) +
+             (["-Xptxas", "-v"] if verbose else []))
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
@@ -69,4 +74,6 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv,
+                variant=_variant, defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

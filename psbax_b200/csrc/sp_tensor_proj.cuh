@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   using M = TpCols<NCH>;        // tensor-memory map
   constexpr int TILES = M::TILES;
   constexpr int NSA = M::NSA;
+  constexpr int GR = NCH == 1 ? 2 : 1;  // producer groups taking alternate blocks (see the producers)
   static_assert(!(PAIRX && TILES != 2), "the packed-FP32 kernel rows pair the two row tiles of a pass");
   extern __shared__ __align__(128) uint8_t tp_smem[];
   uint8_t* const smem = tp_smem;
@@ -282,9 +283,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       sBias[i] = i < lay.Lp_ft ? __ldg(a.pack + lay.off_ft + (size_t)i * OS + dp4) : 0.f;
   if (tid == 0) {
     // the producers read the streamed table block, so they release the stage too
-    for (int i = 0; i < TP_NSB_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1 + TC_NPROD); }
-    for (int i = 0; i < NSA; ++i) { mbar_init(&a_full[i], TC_NPROD); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], TC_NPROD); }
+    // a block is produced by one group of TC_NPROD / GR warps (see the producers)
+    for (int i = 0; i < TP_NSB_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1 + TC_NPROD / GR); }
+    for (int i = 0; i < NSA; ++i) { mbar_init(&a_full[i], TC_NPROD / GR); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], TC_NPROD / GR); }
     mbar_init(x_full, TC_NPROD); mbar_init(x_empty, 1);
     mbar_init(d_full, 1);        mbar_init(d_empty, TC_NEPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -446,11 +448,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     }
   } else if (warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_NPROD) {
     // ================= producers =================
-    const int q = warp & 3, h = (warp - TC_PROD_WARP0) >> 2;  // h: which 8 features; also which X part
+    // Two groups of eight warps (two per lane quarter) take ALTERNATE blocks: group g owns the blocks
+    // with (it & 1) == g, i.e. Z buffer g and the A stages of parity g, and a warp evaluates 16
+    // features (8 of an exact-kernel block) of its block.  With all sixteen warps on every block
+    // (8 features each) a block's fixed latencies — z_full wait, tcgen05.ld, a_empty wait, tcgen05.st,
+    // wait::st, arrive: ~850 cycles — sat on every warp's path for 512 cycles' worth of MUFU per
+    // scheduler, and the warps of a scheduler went through them in step (clock trace, d = 10:
+    // 1450 cycles per block).  Now one group waits while the other evaluates.
+    const int q = warp & 3, h = (warp - TC_PROD_WARP0) >> 2;  // h: which X part this warp writes
+    // (GR = 1 in the one-tile / several-chunk shape: there the blocks are tensor-bound and a warp's
+    // 8 features x 4 A stages already cover the latencies; measured 1.09 -> 1.22 ms at C3 with two groups)
+    const int g = h % GR, h2 = h / GR;                       // group; which part of the block's features
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     constexpr int PT = TC_NPROD * 32;
     const int ptid = tid - TC_PROD_WARP0 * 32;
-    uint32_t it = 0, bs = 0, bph = 0;
+    const bool tracer = q == 0 && h2 == 0;  // warp 0 (and, with two groups, warp 4 for the odd blocks)
+    (void)tracer;
+    uint32_t it = 0, bsc = 0, bphc = 0;
     for (int pass = t0; pass < t1; ++pass) {
       const uint32_t pl = (uint32_t)(pass - t0);
       // ---- X operand of this pass: warp h writes tile (h >> 1), split (h & 1) of its rows ----
@@ -492,84 +506,108 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       if (lane == 0) mbar_arrive(x_full);
 
       for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t bs = bsc, bph = bphc;  // ring stage of block it (every warp counts every block)
+        if (++bsc == NSB) { bsc = 0; bphc ^= 1; }
+        if (GR > 1 && (it & 1u) != (uint32_t)g) continue;
         const uint32_t as = it % NSA, aph = (it / NSA) & 1, zb = it & 1, zph = (it >> 1) & 1;
-        const int kbase = kb * TP_TKB + h * 8;
-        // ---- arguments of this warp's 8 features x TILES tiles from the projection ----
-        if (warp == 0) TC_TRACE(1, it, 0);
+        const int kbase = kb * TP_TKB + h2 * (8 * GR);
+        if (tracer) TC_TRACE(1, it, 0);
         mbar_wait_hybrid_backoff(&z_full[zb], zph, lane);
         tc_fence_after();
-        if (warp == 0) TC_TRACE(1, it, 1);
+        if (tracer) TC_TRACE(1, it, 1);
         const bool kblk = kb >= nkb_r;  // exact-kernel block (KF rows, 3xTF32): no projection arguments to read
-        uint32_t z[TILES][8];
         if (!kblk) {
+          // ---- arguments of this warp's 16 features x TILES tiles from the projection ----
+          uint32_t z[GR][TILES][8];
 #pragma unroll
-          for (int t = 0; t < TILES; ++t) tc_ld8(lane_addr + M::Z + (zb * TILES + t) * 32 + h * 8, z[t]);
-          tc_wait_ld();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&z_empty[zb]);
-        if (warp == 0) TC_TRACE(1, it, 2);
-        // the two MMA operands of this warp's features: 8 features as bf16 pairs (split 1 | split 2) or,
-        // in an exact-kernel block, 4 features as TF32 (hi | lo) — the same 4 + 4 tensor-memory columns
-        uint32_t s1[TILES][4], s2[TILES][4];
-        if (!kblk) {
-          float v[TILES][8];
-          if (kbase < lay.Lp_ft) {
-            const bool lin = kbase >= lay.Lcos;
-            float arg[TILES][8];
+          for (int sg = 0; sg < GR; ++sg)
 #pragma unroll
             for (int t = 0; t < TILES; ++t)
+              tc_ld8(lane_addr + M::Z + (zb * TILES + t) * 32 + h2 * (8 * GR) + sg * 8, z[sg][t]);
+          tc_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&z_empty[zb]);
+            mbar_arrive(&b_empty[bs]);  // (cos / linear blocks read nothing from the operand stage)
+          }
+          if (tracer) TC_TRACE(1, it, 2);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) arg[t][j] = __uint_as_float(z[t][j]);
-            if (!bias_in_x) {  // d % 8 == 0: the bias is not part of the projection
-              const float4 b0 = *reinterpret_cast<const float4*>(sBias + kbase);
-              const float4 b1 = *reinterpret_cast<const float4*>(sBias + kbase + 4);
-              const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          for (int sg = 0; sg < GR; ++sg) {
+            const int kb8 = kbase + sg * 8;
+            float v[TILES][8];
+            if (kb8 < lay.Lp_ft) {
+              const bool lin = kb8 >= lay.Lcos;
+              float arg[TILES][8];
 #pragma unroll
               for (int t = 0; t < TILES; ++t)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) arg[t][j] += bj[j];
+                for (int j = 0; j < 8; ++j) arg[t][j] = __uint_as_float(z[sg][t][j]);
+              if (!bias_in_x) {  // d % 8 == 0: the bias is not part of the projection
+                const float4 b0 = *reinterpret_cast<const float4*>(sBias + kb8);
+                const float4 b1 = *reinterpret_cast<const float4*>(sBias + kb8 + 4);
+                const float bj[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int t = 0; t < TILES; ++t)
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) arg[t][j] += bj[j];
+              }
+#pragma unroll
+              for (int t = 0; t < TILES; ++t)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[t][j] = lin ? arg[t][j] : __cosf(arg[t][j]);
+            } else {  // padding rows between the RFF section and the first exact-kernel block (zero weights)
+#pragma unroll
+              for (int t = 0; t < TILES; ++t)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[t][j] = 0.f;
+            }
+            // ---- BF16x3 split: 8 features as bf16 pairs (split 1 | split 2) ----
+            uint32_t s1[TILES][4], s2[TILES][4];
+#pragma unroll
+            for (int t = 0; t < TILES; ++t)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t p1 = cvt_bf16x2(v[t][2 * c + 1], v[t][2 * c]);
+                const uint64_t rr = ffma2(pack2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u)),
+                                          pack2(-1.0f, -1.0f), pack2(v[t][2 * c], v[t][2 * c + 1]));
+                float r0, r1;
+                unpack2(rr, r0, r1);
+                s1[t][c] = p1;
+                s2[t][c] = cvt_bf16x2(r1, r0);
+              }
+            if (sg == 0) {
+              if (tracer) TC_TRACE(1, it, 3);
+              mbar_wait_hybrid_backoff(&a_empty[as], aph ^ 1, lane);
+              tc_fence_after();
+              if (tracer) TC_TRACE(1, it, 4);
             }
 #pragma unroll
-            for (int t = 0; t < TILES; ++t)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[t][j] = lin ? arg[t][j] : __cosf(arg[t][j]);
-          } else {  // padding rows between the RFF section and the first exact-kernel block (zero weights)
-#pragma unroll
-            for (int t = 0; t < TILES; ++t)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[t][j] = 0.f;
+            for (int t = 0; t < TILES; ++t) {
+              const uint32_t col = M::A + (as * TILES + t) * 32 + h2 * (4 * GR) + sg * 4;
+              tc_st4(lane_addr + col, s1[t]);
+              tc_st4(lane_addr + col + 16, s2[t]);
+            }
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&b_empty[bs]);
-          // ---- BF16x3 split ----
-#pragma unroll
-          for (int t = 0; t < TILES; ++t)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t p1 = cvt_bf16x2(v[t][2 * c + 1], v[t][2 * c]);
-              const uint64_t rr = ffma2(pack2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u)),
-                                        pack2(-1.0f, -1.0f), pack2(v[t][2 * c], v[t][2 * c + 1]));
-              float r0, r1;
-              unpack2(rr, r0, r1);
-              s1[t][c] = p1;
-              s2[t][c] = cvt_bf16x2(r1, r0);
-            }
         } else {
-          // ---- exact-kernel block: KF = 16 features, 4 per warp (FFMA path: r^2 as a sum of squared
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&z_empty[zb]);
+          if (tracer) TC_TRACE(1, it, 2);
+          // ---- exact-kernel block: KF = 16 features, KW = 8 per warp (FFMA path: r^2 as a sum of squared
           // differences), TF32 hi | lo operands ----
           // the block's table rows sit behind the [W;V] images of the same stage
+          constexpr int KW = 4 * GR;
           mbar_wait_hybrid_backoff(&b_full[bs], bph, lane);
-          const float* ft = reinterpret_cast<const float*>(sB + bs * STAGE + sl.ftk) + (size_t)(h * 4) * OS;
-          float acc[TILES][4];
+          const float* ft = reinterpret_cast<const float*>(sB + bs * STAGE + sl.ftk) + (size_t)(h2 * KW) * OS;
+          float acc[TILES][KW];
           if constexpr (PAIRX) {
             // packed FP32 over the thread's (tile 0, tile 1) rows; inv_ls and the table entry enter as
             // scalar-broadcast operands:  df = x * inv_ls + (-x_t * inv_ls),  acc += df * df
             const uint64_t* xr = reinterpret_cast<const uint64_t*>(sX) + q * 32 + lane;
-            uint64_t acc2[4];
+            uint64_t acc2[KW];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc2[j] = 0ull;
+            for (int j = 0; j < KW; ++j) acc2[j] = 0ull;
             for (int i0 = 0; i0 < dp4; i0 += 4) {
               uint64_t xa[4];
               float il4[4];
@@ -579,7 +617,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
                 il4[c] = sIl[i0 + c];
               }
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < KW; ++j) {
                 const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
                 const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
@@ -590,19 +628,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
               }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) unpack2(acc2[j], acc[0][j], acc[TILES - 1][j]);
+            for (int j = 0; j < KW; ++j) unpack2(acc2[j], acc[0][j], acc[TILES - 1][j]);
           } else if constexpr (TILES == 1) {
             // one row per thread: packed FP32 over PAIRS OF DIMENSIONS.  The scaled row sits in shared
             // memory as (x_i, x_i+1) / ls pairs, a table row is read as 16-byte pieces = two pairs:
             //   df = (x_i, x_i+1) / ls + (-x_t)[i, i+1] / ls,  (acc_even, acc_odd) += df * df,  r^2 = acc_even + acc_odd
             const uint64_t* xs2 = reinterpret_cast<const uint64_t*>(sX) + q * 32 + lane;
-            uint64_t acc2[4] = {0ull, 0ull, 0ull, 0ull};
+            uint64_t acc2[KW];
+#pragma unroll
+            for (int j = 0; j < KW; ++j) acc2[j] = 0ull;
             const uint64_t one2 = pack2(1.0f, 1.0f);
-#pragma unroll 2
             for (int i0 = 0; i0 < dp4; i0 += 4) {
               const uint64_t xa = xs2[(i0 >> 1) * TM], xb = xs2[((i0 >> 1) + 1) * TM];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < KW; ++j) {
                 const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(ft + j * OS + i0);
                 const uint64_t dfa = ffma2(xa, one2, w.x), dfb = ffma2(xb, one2, w.y);
                 acc2[j] = ffma2(dfa, dfa, acc2[j]);
@@ -610,7 +649,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
               }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < KW; ++j) {
               float ev, od;
               unpack2(acc2[j], ev, od);
               acc[0][j] = ev + od;
@@ -620,7 +659,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
 #pragma unroll
             for (int t = 0; t < TILES; ++t)
 #pragma unroll
-              for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+              for (int j = 0; j < KW; ++j) acc[t][j] = 0.f;
             for (int i0 = 0; i0 < dp4; i0 += 4) {
               float xa[TILES][4];
 #pragma unroll
@@ -628,7 +667,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
 #pragma unroll
                 for (int c = 0; c < 4; ++c) xa[t][c] = xs[(t * dp4 + i0 + c) * TM] * sIl[i0 + c];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < KW; ++j) {
                 const float4 w4 = *reinterpret_cast<const float4*>(ft + j * OS + i0);
                 const float wv4[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
@@ -643,35 +682,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(&b_empty[bs]);
+          if (tracer) TC_TRACE(1, it, 3);
+          mbar_wait_hybrid_backoff(&a_empty[as], aph ^ 1, lane);
+          tc_fence_after();
+          if (tracer) TC_TRACE(1, it, 4);
 #pragma unroll
           for (int t = 0; t < TILES; ++t) {
-            float kv[4];
-            kernel_profile_n<4>(acc[t], kv, lay.kernel);
+            float kv[KW];
+            kernel_profile_n<KW>(acc[t], kv, lay.kernel);
+            uint32_t khi[KW], klo[KW];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < KW; ++j) {
               const uint32_t hb = __float_as_uint(kv[j]) & 0xffffe000u;
-              s1[t][j] = hb;
-              s2[t][j] = __float_as_uint(kv[j] - __uint_as_float(hb));
+              khi[j] = hb;
+              klo[j] = __float_as_uint(kv[j] - __uint_as_float(hb));
+            }
+            const uint32_t col = M::A + (as * TILES + t) * 32 + h2 * KW;
+            if constexpr (KW == 8) {
+              tc_st8(lane_addr + col, khi);
+              tc_st8(lane_addr + col + 16, klo);
+            } else {
+              tc_st4(lane_addr + col, khi);
+              tc_st4(lane_addr + col + 16, klo);
             }
           }
-        }
-        if (warp == 0) TC_TRACE(1, it, 3);
-        mbar_wait_hybrid_backoff(&a_empty[as], aph ^ 1, lane);
-        tc_fence_after();
-        if (warp == 0) TC_TRACE(1, it, 4);
-#pragma unroll
-        for (int t = 0; t < TILES; ++t) {
-          const uint32_t col = M::A + (as * TILES + t) * 32 + h * 4;
-          tc_st4(lane_addr + col, s1[t]);
-          tc_st4(lane_addr + col + 16, s2[t]);
         }
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[as]);
-        if (warp == 0) TC_TRACE(1, it, 5);
-        if (lane == 0 && (warp == 5 || warp == 10 || warp == 15)) TC_TRACE(3, it, 1 + warp / 5);  // other producers: stored
-        if (++bs == NSB) { bs = 0; bph ^= 1; }
+        if (tracer) TC_TRACE(1, it, 5);
       }
     }
   } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_NEPI) {
