@@ -59,7 +59,7 @@ __host__ __device__ inline uint32_t tp_obytes(int d) { return 2u * 32u * (uint32
 struct TpSmem {
   // `b`: ring of `nsb` stages = nch [W;V] images | Omega_aug images | the block's rows of the feature
   // table (only when the problem has exact-kernel rows; copied only for blocks that contain them)
-  uint32_t b, stage, nsb, ftk, x, out, state, state_stride, il, bias, bars, total;
+  uint32_t b, stage, nsb, ftk, x, out, state, state_stride, il, bias, seq, bars, total;
 };
 __host__ __device__ inline TpSmem tp_smem_layout(const Layout& l, int epi, int k, int nch = 1) {
   TpSmem s{};
@@ -71,8 +71,9 @@ __host__ __device__ inline TpSmem tp_smem_layout(const Layout& l, int epi, int k
   // its contraction completes and a bulk copy takes ~2000 cycles, so depth 4 starved the issuers)
   const uint32_t xbytes = l.n > 0 ? tiles * l.dp4 * TM * 4 : 0u;
   const uint32_t obytes = tiles * TN * OUT_LD * 4;  // staging: both tiles (NCH = 1) / one chunk at a time
+  const uint32_t seqbytes = (uint32_t)round_up((l.nkb_r + l.nkb_k) * 2, 16);  // block order of a pass (uint16 per block)
   const uint32_t fixed = xbytes + obytes + (uint32_t)nch * s.state_stride + (uint32_t)round_up(l.dp4, 4) * 4 +
-                         (tp_bias_in_x(l.d) ? 0u : (uint32_t)l.Kp * 4) + 16 + 40 * 8;
+                         (tp_bias_in_x(l.d) ? 0u : (uint32_t)l.Kp * 4) + seqbytes + 16 + 40 * 8;
   uint32_t nsb = fixed < 227u * 1024u ? (227u * 1024u - fixed) / s.stage : 0u;
   s.nsb = nsb > (uint32_t)TP_NSB_MAX ? (uint32_t)TP_NSB_MAX : nsb;
   uint32_t o = 0;
@@ -83,6 +84,7 @@ __host__ __device__ inline TpSmem tp_smem_layout(const Layout& l, int epi, int k
   s.il = o;    o += (uint32_t)round_up(l.dp4, 4) * 4;
   s.bias = o;  o += tp_bias_in_x(l.d) ? 0u : (uint32_t)l.Kp * 4;       // per-feature bias (d % 8 == 0)
   o = (o + 15) / 16 * 16;
+  s.seq = o;   o += seqbytes;
   s.bars = o;  o += 40 * 8;
   s.total = o;
   return s;
@@ -210,13 +212,62 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
+// Order of a pass's blocks.  In the one-tile / several-chunk shape (S > 64) the cos / linear blocks
+// (tensor-heavy, little producer work) and the exact-kernel blocks (FFMA / shared-memory heavy, little
+// tensor work) are INTERLEAVED so that the two kinds overlap in the pipeline instead of running as two
+// phases: runs of `s` cos blocks followed by `t` exact-kernel blocks (one of s, t is 1), the surplus
+// of the longer kind at the end (C3 top-10: 1.07 -> 1.00 ms).  In the two-tile shape the contraction
+// is issued in order behind a slow exact-kernel block with only two A stages to run ahead in, and the
+// interleaved order lost 4 % (C5): there the exact-kernel blocks stay at the end of the pass.
+// Every role walks the same sequence; idx is the block's image index in pack order (cos blocks
+// first, then the exact-kernel blocks).
+#ifndef TP_PAIRX_MIN_DP4
+#define TP_PAIRX_MIN_DP4 8  // packed-FP32 exact-kernel rows over the row pair from this padded d on
+#endif
+#ifndef TP_INTERLEAVE
+#define TP_INTERLEAVE 1
+#endif
+// The order is tabulated once per CTA in shared memory (uint16 per position: bit 15 = exact-kernel
+// block, low bits = image index): the roles then pay one LDS per block (walking the sequence with
+// counters cost every warp ~25 instructions per block, 3-5 % of the C5 kernel).
+__device__ __forceinline__ uint16_t tp_seq_entry(int p, int nr, int nk, bool il) {
+  if (!TP_INTERLEAVE || !il || nr == 0 || nk == 0) return (uint16_t)(p | (p >= nr ? 0x8000 : 0));
+  const int s = nr > nk ? nr / nk : 1, t = nk > nr ? nk / nr : 1;
+  const int G = min(nr / s, nk / t);  // complete runs of (s cos, t exact-kernel) blocks
+  if (p < G * (s + t)) {
+    const int g = p / (s + t), o = p - g * (s + t);
+    return o < s ? (uint16_t)(g * s + o) : (uint16_t)((nr + g * t + (o - s)) | 0x8000);
+  }
+  const int q = p - G * (s + t), rl = nr - G * s;  // the surplus: cos blocks first
+  return q < rl ? (uint16_t)(G * s + q) : (uint16_t)((nr + G * t + (q - rl)) | 0x8000);
+}
+struct TpSeq {
+  const uint16_t* tab;
+  int n, pos;
+  __device__ __forceinline__ TpSeq(const uint16_t* tab_, int n_) : tab(tab_), n(n_), pos(0) {}
+  // advance to the next block of the sequence: is it an exact-kernel block, and its image index
+  __device__ __forceinline__ bool next(int* idx) {
+    const uint32_t e = tab[pos];
+    pos = (pos + 1 == n) ? 0 : pos + 1;
+    *idx = (int)(e & 0x7fffu);
+    return (e & 0x8000u) != 0;
+  }
+};
+
 template <int EPI, bool PAIRX, int NCH>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_constant__ KArgs a, size_t off_om) {
   using C = TcCfg<true, true>;  // BF16x3 contraction with 32-feature blocks
   using M = TpCols<NCH>;        // tensor-memory map
   constexpr int TILES = M::TILES;
   constexpr int NSA = M::NSA;
-  constexpr int GR = NCH == 1 ? 2 : 1;  // producer groups taking alternate blocks (see the producers)
+  // Producer groups taking blocks in turn (see the producers): two in the two-tile shape.  In the one-tile /
+  // several-chunk shape (S > 64) every warp works on every block: the operand ring there is 3 stages of
+  // 42 KB (C3), a block's operands arrive ~2 k cycles after the stage is released, and groups working
+  // on different blocks wait for their stage instead of overlapping (tried: 2 and 4 groups with a
+  // 4 x 2 / 4 x 4 register-blocked exact-kernel path, C3 1.1 -> 1.4 / 1.7 ms).
+  constexpr int GR = NCH == 1 ? 2 : 1;
+  static_assert(NSA % GR == 0, "a group owns the A stages of its blocks");
+  constexpr int ZB = GR > 2 ? GR : 2;  // Z barrier pairs (see below)
   static_assert(!(PAIRX && TILES != 2), "the packed-FP32 kernel rows pair the two row tiles of a pass");
   extern __shared__ __align__(128) uint8_t tp_smem[];
   uint8_t* const smem = tp_smem;
@@ -232,13 +283,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   uint64_t* b_empty = bars + 8;    // [8]
   uint64_t* a_full = bars + 16;    // [4]
   uint64_t* a_empty = bars + 20;   // [4]
-  uint64_t* z_full = bars + 24;    // [2]
-  uint64_t* z_empty = bars + 26;   // [2]
-  uint64_t* x_full = bars + 28;
-  uint64_t* x_empty = bars + 29;
-  uint64_t* d_full = bars + 30;
-  uint64_t* d_empty = bars + 31;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 32);
+  // Z: two tensor-memory buffers (block it -> buffer it & 1) but ZB = max(2, GR) barrier pairs
+  // (block it -> pair it % ZB): a producer group only ever waits on its own pair, so it sees every
+  // completion of that barrier in order (with one pair per buffer a group that skips a completion
+  // cannot tell "not yet" from "already twice" by the phase parity)
+  uint64_t* z_full = bars + 24;    // [4]
+  uint64_t* z_empty = bars + 28;   // [4]
+  uint64_t* x_full = bars + 32;
+  uint64_t* x_empty = bars + 33;
+  uint64_t* d_full = bars + 34;
+  uint64_t* d_empty = bars + 35;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 36);
   const uint32_t NSB = sl.nsb;
 
   const int d = lay.d, OS = lay.OS, dp4 = lay.dp4;
@@ -258,6 +313,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
   auto epi_of = [&](int c) { return epi_carve(reinterpret_cast<float*>(smem + sl.state + c * sl.state_stride), EPI, a.k); };
 
   for (int i = tid; i < round_up(dp4, 4); i += TC_THREADS) sIl[i] = __ldg(a.pack + lay.off_invls + i);
+  uint16_t* sSeq = reinterpret_cast<uint16_t*>(smem + sl.seq);
+  for (int i = tid; i < nkb; i += TC_THREADS) sSeq[i] = tp_seq_entry(i, nkb_r, lay.nkb_k, NCH > 1);
   // x tile of the exact-kernel rows: [i][row] (tile 0, tile 1) pairs for the packed-FP32 path, else
   // [tile][i][row] for the scalar path.  A template parameter, not a runtime branch: at the
   // 80-register cap the mere presence of the second path cost the cos path 10 % (spills).
@@ -286,7 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     // a block is produced by one group of TC_NPROD / GR warps (see the producers)
     for (int i = 0; i < TP_NSB_MAX; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1 + TC_NPROD / GR); }
     for (int i = 0; i < NSA; ++i) { mbar_init(&a_full[i], TC_NPROD / GR); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], TC_NPROD / GR); }
+    for (int i = 0; i < ZB; ++i) { mbar_init(&z_full[i], 1); mbar_init(&z_empty[i], TC_NPROD / GR); }
     mbar_init(x_full, TC_NPROD); mbar_init(x_empty, 1);
     mbar_init(d_full, 1);        mbar_init(d_empty, TC_NEPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -313,9 +370,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     const uint8_t* gFT = reinterpret_cast<const uint8_t*>(a.pack + lay.off_ft);
     const uint32_t obytes = tp_obytes(d);
     const uint32_t wbytes = (uint32_t)nch * TP_WBYTES;
-    uint32_t kb = 0, bs = 0, ph = 0;  // block inside the pass; ring stage and its phase
+    uint32_t bs = 0, ph = 0;  // ring stage and its phase
+    TpSeq seq(sSeq, nkb);
     for (uint32_t it = 0; it < total_blocks; ++it) {
-      const bool kblk = (int)kb >= nkb_r;  // exact-kernel block: [W;V] images (tf32) + its KF table rows, no projection
+      int kb;  // image index of this block
+      const bool kblk = seq.next(&kb);  // exact-kernel block: [W;V] images (tf32) + its KF table rows, no projection
       TC_TRACE(3, it, 0);
       mbar_wait_hybrid_backoff<200>(&b_empty[bs], ph ^ 1, lane);
       TC_TRACE(3, it, 1);
@@ -330,7 +389,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           bulk_g2s(sB + bs * STAGE + NCH * TP_WBYTES, gO + (size_t)kb * obytes, obytes, &b_full[bs]);
       }
       __syncwarp();
-      if (++kb == (uint32_t)nkb) kb = 0;
       if (++bs == NSB) { bs = 0; ph ^= 1; }
     }
   } else if (warp == TP_WARP_PROJ) {
@@ -349,11 +407,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     const int nks = kx / 8;
     const uint32_t nkb1 = (uint32_t)nkb - 1;
     uint32_t jkb = 0, pl = 0, bs = 0, bph = 0;
+    TpSeq seq(sSeq, nkb);
     for (uint32_t jt = 0; jt < total_blocks; ++jt) {
       const uint32_t zb = jt & 1;
+      int bidx;
+      const bool kblk = seq.next(&bidx);
       if (jkb == 0) mbar_wait(x_full, pl & 1);  // this pass's X operand is in tensor memory
       mbar_wait(&b_full[bs], bph);
-      mbar_wait(&z_empty[zb], ((jt >> 1) & 1) ^ 1);
+      if (jt >= 2) mbar_wait(&z_empty[(jt - 2) % ZB], ((jt - 2) / ZB) & 1);  // block jt - 2 has left this Z buffer
       __syncwarp();
       tc_fence_after();
       TC_TRACE(0, jt, 4);
@@ -361,7 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
         const uint64_t oh0 = dO0 + (uint64_t)(bs * stage16), ol0 = oh0 + osplit16;
         // exact-kernel blocks have no projection: only the barrier protocol runs
 #pragma unroll
-        for (int t = 0; t < ((int)jkb < nkb_r ? TILES : 0); ++t) {
+        for (int t = 0; t < (kblk ? 0 : TILES); ++t) {
           const uint32_t dz = tmem + M::Z + (zb * TILES + t) * 32;
           const uint32_t xh = tmem + M::X + (t * 2) * 32, xl = xh + 32;
           tc_mma_ts(dz, xh, oh0, IDESC_P, 0u);
@@ -375,7 +436,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
             tc_mma_ts(dz, xl + ks * 8, oh, IDESC_P, 1u);
           }
         }
-        tc_commit(&z_full[zb]);
+        tc_commit(&z_full[jt % ZB]);
         if (jkb == nkb1) tc_commit(x_empty);  // last reader of this pass's X
       }
       __syncwarp();
@@ -389,9 +450,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     const uint64_t dW0 = umma_desc_kmajor(smem_u32(sB), 128, C::B_SBO);
     const uint32_t stage16 = STAGE >> 4;
     const uint32_t nkb1 = (uint32_t)nkb - 1;
-    uint32_t kb = 0, pl = 0, bs = 0, bph = 0;
+    uint32_t kb = 0, pl = 0, bs = 0, bph = 0;  // kb: position inside the pass
+    TpSeq seq(sSeq, nkb);
     for (uint32_t it = 0; it < total_blocks; ++it) {
       const bool last = kb == nkb1;
+      int bidx;
+      const bool kblk = seq.next(&bidx);
       const uint32_t as = it % NSA;
       TC_TRACE(0, it, 0);
       if (kb == 0) mbar_wait(d_empty, (pl & 1) ^ 1);
@@ -402,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       TC_TRACE(0, it, 2);
       if (elect_one()) {
         const uint64_t b10 = dW0 + (uint64_t)(bs * stage16);
-        if ((int)kb >= nkb_r) {
+        if (kblk) {
           // exact-kernel block: KF features as TF32 hi | lo (A columns [0, 16) | [16, 32)), K = 8 per MMA
           constexpr uint32_t IDESC_K = umma_idesc_tf32(TN);
           constexpr uint32_t SBO_K = KF * 4 * 8, SPLIT2_K = 8 * SBO_K;
@@ -462,9 +526,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
     constexpr int PT = TC_NPROD * 32;
     const int ptid = tid - TC_PROD_WARP0 * 32;
-    const bool tracer = q == 0 && h2 == 0;  // warp 0 (and, with two groups, warp 4 for the odd blocks)
+    const bool tracer = q == 0 && h2 == 0;  // warp 0 (and, with two groups, warp 4 for its blocks)
     (void)tracer;
     uint32_t it = 0, bsc = 0, bphc = 0;
+    TpSeq seq(sSeq, nkb);
     for (int pass = t0; pass < t1; ++pass) {
       const uint32_t pl = (uint32_t)(pass - t0);
       // ---- X operand of this pass: warp h writes tile (h >> 1), split (h & 1) of its rows ----
@@ -505,17 +570,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(x_full);
 
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
+      for (int pos = 0; pos < nkb; ++pos, ++it) {
         const uint32_t bs = bsc, bph = bphc;  // ring stage of block it (every warp counts every block)
         if (++bsc == NSB) { bsc = 0; bphc ^= 1; }
-        if (GR > 1 && (it & 1u) != (uint32_t)g) continue;
-        const uint32_t as = it % NSA, aph = (it / NSA) & 1, zb = it & 1, zph = (it >> 1) & 1;
+        int kb;  // image index of this block
+        const bool kblk = seq.next(&kb);  // exact-kernel block (KF rows, 3xTF32): no projection arguments to read
+        if (GR > 1 && (it & (uint32_t)(GR - 1)) != (uint32_t)g) continue;
+        const uint32_t as = it % NSA, aph = (it / NSA) & 1, zb = it & 1, zi = it % ZB, zph = (it / ZB) & 1;
         const int kbase = kb * TP_TKB + h2 * (8 * GR);
         if (tracer) TC_TRACE(1, it, 0);
-        mbar_wait_hybrid_backoff(&z_full[zb], zph, lane);
+        mbar_wait_hybrid_backoff(&z_full[zi], zph, lane);
         tc_fence_after();
         if (tracer) TC_TRACE(1, it, 1);
-        const bool kblk = kb >= nkb_r;  // exact-kernel block (KF rows, 3xTF32): no projection arguments to read
         if (!kblk) {
           // ---- arguments of this warp's 16 features x TILES tiles from the projection ----
           uint32_t z[GR][TILES][8];
@@ -528,7 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive(&z_empty[zb]);
+            mbar_arrive(&z_empty[zi]);
             mbar_arrive(&b_empty[bs]);  // (cos / linear blocks read nothing from the operand stage)
           }
           if (tracer) TC_TRACE(1, it, 2);
@@ -592,10 +658,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
         } else {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&z_empty[zb]);
+          if (lane == 0) mbar_arrive(&z_empty[zi]);
           if (tracer) TC_TRACE(1, it, 2);
-          // ---- exact-kernel block: KF = 16 features, KW = 8 per warp (FFMA path: r^2 as a sum of squared
-          // differences), TF32 hi | lo operands ----
+          // ---- exact-kernel block: KF = 16 features, KW = 4 GR per warp (FFMA path: r^2 as a sum of
+          // squared differences), TF32 hi | lo operands.  (All sixteen warps on these blocks, with the
+          // groups alternating on the others only, was slower: nobody works ahead of such a block.) ----
           // the block's table rows sit behind the [W;V] images of the same stage
           constexpr int KW = 4 * GR;
           mbar_wait_hybrid_backoff(&b_full[bs], bph, lane);
@@ -698,7 +765,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
               klo[j] = __float_as_uint(kv[j] - __uint_as_float(hb));
             }
             const uint32_t col = M::A + (as * TILES + t) * 32 + h2 * KW;
-            if constexpr (KW == 8) {
+            if constexpr (KW == 16) {
+              tc_st16(lane_addr + col, khi);
+              tc_st16(lane_addr + col + 16, klo);
+            } else if constexpr (KW == 8) {
               tc_st8(lane_addr + col, khi);
               tc_st8(lane_addr + col + 16, klo);
             } else {
@@ -831,7 +901,7 @@ int tensor_proj_launch_shape(const KArgs& a, int sms, cudaStream_t st, char* err
   // instantiation (same box, d = 5 / 10 / 32).  The level-set kernel (register-resident epilogue
   // state, tightest register budget) only gains from d = 13 on (d = 10: 7.78 -> 8.23 ms, d = 32:
   // 3.01 -> 2.87); top-k and values gain from d = 5 (C5 top-32 8.65 -> 8.48 ms).
-  const bool pairx = a.lay.n > 0 && a.lay.dp4 >= (EPI == EPI_LEVELSET ? 16 : 8);
+  const bool pairx = a.lay.n > 0 && a.lay.dp4 >= TP_PAIRX_MIN_DP4;
   return pairx ? tensor_proj_launch_epi<EPI, true, 1>(a, plan, st, err, errlen)
                : tensor_proj_launch_epi<EPI, false, 1>(a, plan, st, err, errlen);
 }
