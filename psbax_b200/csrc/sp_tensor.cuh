@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
               kernel_profile_n<KW>(r2[t], kv, lay.kernel);
 #pragma unroll
               for (int j = 0; j < KW; ++j) {
-                const uint32_t hb = __float_as_uint(kv[j]) & 0xffffe000u;
+                const uint32_t hb = (__float_as_uint(kv[j]) + 0x1000u) & 0xffffe000u;  // round to TF32: |lo| <= 2^-11 |x|, unbiased
                 khi[t][j] = hb;
                 klo[t][j] = __float_as_uint(kv[j] - __uint_as_float(hb));
               }
@@ -1009,7 +1009,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const uint32_t hb = __float_as_uint(v[t][j]) & 0xffffe000u;
+                const uint32_t hb = (__float_as_uint(v[t][j]) + 0x1000u) & 0xffffe000u;  // round to TF32
                 s1[g][t][j] = hb;
                 s2[g][t][j] = __float_as_uint(v[t][j] - __uint_as_float(hb));
               }

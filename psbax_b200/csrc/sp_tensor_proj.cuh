@@ -186,13 +186,28 @@ inline int tensor_proj_pack(const Layout& l, float* pack, cudaStream_t st) {
 #ifndef TP_BACKOFF
 #define TP_BACKOFF 64
 #endif
+// The fallback poll is a try_wait with a suspend-time hint: the hardware parks the thread until the
+// phase completes or the hint expires.  (__nanosleep between plain try_waits did not hold the pollers
+// back: ncu source view of the C5 kernel, round 2 — the four epilogue lanes waiting for d_full with
+// __nanosleep(500) still executed a probe every ~50 cycles, 16 % of all issued instructions of a
+// kernel whose issue slots are 69 % busy; all poll loops together ~30 %.)
+#ifndef TP_WAIT_HINT
+#define TP_WAIT_HINT 1  // 0: the nanosleep form
+#endif
 template <int NS = TP_BACKOFF>
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
+#if TP_WAIT_HINT
+  constexpr uint32_t HINT = NS >= 200 ? 20000u : 2000u;  // ns
+  while (!mbar_try_wait_hint(bar, parity, HINT)) {
+    if (++spins > (1u << 22)) asm volatile("trap;");
+  }
+#else
   while (!mbar_try_wait(bar, parity)) {
     if (NS > 0) __nanosleep(NS);
     if (++spins > (1u << 24)) asm volatile("trap;");
   }
+#endif
 }
 // as mbar_wait_hybrid, with a backed-off fallback poll (the producers of this kernel have slack).
 // NS is the sleep between probes: the epilogue waits most of a pass for d_full, and at 64 ns its
@@ -212,20 +227,21 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "memory");
 }
 
-// Order of a pass's blocks.  In the one-tile / several-chunk shape (S > 64) the cos / linear blocks
-// (tensor-heavy, little producer work) and the exact-kernel blocks (FFMA / shared-memory heavy, little
-// tensor work) are INTERLEAVED so that the two kinds overlap in the pipeline instead of running as two
-// phases: runs of `s` cos blocks followed by `t` exact-kernel blocks (one of s, t is 1), the surplus
-// of the longer kind at the end (C3 top-10: 1.07 -> 1.00 ms).  In the two-tile shape the contraction
-// is issued in order behind a slow exact-kernel block with only two A stages to run ahead in, and the
-// interleaved order lost 4 % (C5): there the exact-kernel blocks stay at the end of the pass.
-// Every role walks the same sequence; idx is the block's image index in pack order (cos blocks
-// first, then the exact-kernel blocks).
+// Order of a pass's blocks: pack order (cos / linear blocks, then the exact-kernel blocks), tabulated per
+// CTA so that every role walks the same sequence.  TP_INTERLEAVE = 1 alternates runs of `s` cos blocks and
+// `t` exact-kernel blocks in the one-tile / several-chunk shape (S > 64), which overlaps the tensor-heavy
+// and the FFMA / shared-memory-heavy kind in the pipeline (C3 top-10 1.07 -> 1.00 ms) — and is OFF because
+// it costs accuracy: on a Matheron draw ||V_s|| is tens (C3: 50), the partial sums of k(x, X) . V_s are
+// large until the last exact-kernel block has cancelled them, and with the cos blocks accumulated in
+// between, every one of their (many) MMAs rounds the fp32 accumulators at that magnitude: max value
+// error 1.2 x the strict tolerance at C3 against 0.69 x in pack order (scripts/c3_err_probe.py).
+// (Two-tile shape: interleaving also lost 4 % at C5 — the contraction is issued in order behind a slow
+// exact-kernel block with only two A stages to run ahead in.)
 #ifndef TP_PAIRX_MIN_DP4
 #define TP_PAIRX_MIN_DP4 8  // packed-FP32 exact-kernel rows over the row pair from this padded d on
 #endif
 #ifndef TP_INTERLEAVE
-#define TP_INTERLEAVE 1
+#define TP_INTERLEAVE 0
 #endif
 // The order is tabulated once per CTA in shared memory (uint16 per position: bit 15 = exact-kernel
 // block, low bits = image index): the roles then pay one LDS per block (walking the sequence with
@@ -760,7 +776,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
             uint32_t khi[KW], klo[KW];
 #pragma unroll
             for (int j = 0; j < KW; ++j) {
-              const uint32_t hb = __float_as_uint(kv[j]) & 0xffffe000u;
+              const uint32_t hb = (__float_as_uint(kv[j]) + 0x1000u) & 0xffffe000u;  // round to TF32: |lo| <= 2^-11 |x|, unbiased
               khi[j] = hb;
               klo[j] = __float_as_uint(kv[j] - __uint_as_float(hb));
             }
