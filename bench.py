@@ -450,7 +450,7 @@ class Ctx:
 
 def timed_steps(ctx, step, K, flush=False):
     """K steps, each bracketed by CUDA events on the launching stream; barrier + synchronize on both
-    sides.  Returns (span seconds [first start .. last end, minus flushes when flushing], per-step ms list)."""
+    sides.  Returns (device seconds of the K steps, per-step ms list, wall seconds, last result)."""
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     ctx.sync_all()
     t0 = time.perf_counter()
@@ -464,7 +464,10 @@ def timed_steps(ctx, step, K, flush=False):
     ctx.sync_all()
     wall = time.perf_counter() - t0
     ms = [a.elapsed_time(b) for a, b in evs]
-    span = sum(ms) / 1e3 if flush else evs[0][0].elapsed_time(evs[-1][1]) / 1e3
+    # device time of exactly K steps: the sum of the per-step event spans (with inputs larger than L2 the steps
+    # run back to back and this equals first-start .. last-end; a host-side stall between two launches — seen
+    # once at 2 GPUs: one 77 ms gap in ten 8 ms steps — is then visible in wall_ms_per_step, not in the metric)
+    span = sum(ms) / 1e3
     return span, ms, wall, out
 
 
