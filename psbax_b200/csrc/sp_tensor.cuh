@@ -46,6 +46,48 @@ constexpr int TC_MAX_S = 1 << 20;  // any S: processed in chunks of 64 samples
 #ifndef PSBAX_TC_NPROD
 #define PSBAX_TC_NPROD 16
 #endif
+#ifndef PSBAX_TC_GROUPS
+#define PSBAX_TC_GROUPS 1  // producer groups of the register-x BF16x3 kernel taking alternate blocks (1: every warp on every block)
+#endif
+#ifndef PSBAX_TC_ISSUER_HINT
+#define PSBAX_TC_ISSUER_HINT 0  // suspend-time hint (ns) of the MMA issuer's and the loader's barrier waits; 0 = plain try_wait
+#endif
+#ifndef PSBAX_TC_XPREFETCH
+#define PSBAX_TC_XPREFETCH 0  // (measured: no gain; costs registers) register-x kernels: the next pass's candidate rows are loaded during the current pass
+#endif
+#ifndef PSBAX_TC_DEFER
+#define PSBAX_TC_DEFER 0  // (measured: no gain, 8.24 -> 8.30 ms) register-x kernels: a block's tcgen05.wait::st + a_full arrive are issued inside the next block's math
+#endif
+#ifndef PSBAX_TC_STAGGER
+#define PSBAX_TC_STAGGER 0  // cycles of start offset between the producer warps of one scheduler
+#endif
+#ifndef PSBAX_EXP_NOLDS
+#define PSBAX_EXP_NOLDS 0
+#endif
+#ifndef PSBAX_EXP_NOCOS
+#define PSBAX_EXP_NOCOS 0
+#endif
+#ifndef PSBAX_EXP_NOSTTM
+#define PSBAX_EXP_NOSTTM 0
+#endif
+#ifndef PSBAX_EXP_NOEPI
+#define PSBAX_EXP_NOEPI 0
+#endif
+#ifndef PSBAX_EXP_NOCOPY
+#define PSBAX_EXP_NOCOPY 0
+#endif
+#ifndef PSBAX_EXP_FREERUN
+#define PSBAX_EXP_FREERUN 0  // what-if build (wrong results): producers alone, no barriers, every other role idle
+#endif
+#ifndef PSBAX_EXP_NOAEMPTY
+#define PSBAX_EXP_NOAEMPTY 0  // what-if build (wrong results): producers never wait for their A stage
+#endif
+#ifndef PSBAX_EXP_NOMMA
+#define PSBAX_EXP_NOMMA 0
+#endif
+#ifndef PSBAX_SPLIT_FHFMA
+#define PSBAX_SPLIT_FHFMA 1  // BF16 residuals by mixed-precision FMA (0: unpack + packed subtract, the round-1 form)
+#endif
 // Operand-format / block-size configuration.  GEN = generic-d kernel (x tile in shared memory).
 template <bool BF, bool GEN>
 struct TcCfg {
@@ -211,6 +253,18 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
+// all lanes wait (the warp stays converged) with a suspend-time hint: fewer probes from a warp that only waits
+template <int NS>
+__device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
+  if constexpr (NS > 0) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, NS)) {
+      if (++spins > (1u << 24)) asm volatile("trap;");
+    }
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
 #ifndef PSBAX_AEMPTY_HINT
 #define PSBAX_AEMPTY_HINT 0  // measured: 0 (plain try_wait), 300, 1000, 5000 ns all 7.82 ms
 #endif
@@ -286,6 +340,18 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(float a, float b) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b));
   return d;
 }
+// residuals of a packed bf16 pair against its fp32 sources, one mixed-precision FMA each (FHFMA.BF16 on
+// sm_100: the bf16 half is an operand selector, so neither the unpack nor a packed subtract is needed):
+// r_lo = v_lo - bf16_lo(p), r_hi = v_hi - bf16_hi(p)
+__device__ __forceinline__ void bf16_residual2(uint32_t p, float v_lo, float v_hi, float& r_lo, float& r_hi) {
+  asm("{\n\t.reg .b16 l, h, m;\n\t"
+      "mov.b32 {l, h}, %2;\n\t"
+      "mov.b16 m, 0xBF80;\n\t"  // -1.0
+      "fma.rn.f32.bf16 %0, l, m, %3;\n\t"
+      "fma.rn.f32.bf16 %1, h, m, %4;\n\t}"
+      : "=f"(r_lo), "=f"(r_hi)
+      : "r"(p), "f"(v_lo), "f"(v_hi));
+}
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
@@ -330,14 +396,23 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int N) {
 
 // clock trace (compile with -DPSBAX_TC_TRACE=1): role r (0 = MMA, 1 = first producer warp,
 // 2 = first epilogue warp, 3 = loader), CTA 0 only.  Compiled out of the production build.
+// PSBAX_TC_TRACE=2: the four producer warps of lane quarter 0 (one scheduler) as roles 0..3 instead.
 #if defined(PSBAX_TC_TRACE) && PSBAX_TC_TRACE
-#define TC_TRACE(role, it, slot)                                                         \
+#define TC_TRACE_RAW(role, it, slot)                                                     \
   do {                                                                                   \
     if (a.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (it) < 128)          \
       a.trace[((role) * 128 + (it)) * 8 + (slot)] = clock64();                           \
   } while (0)
+#if PSBAX_TC_TRACE == 2
+#define TC_TRACE(role, it, slot) do { } while (0)
+#define TC_TRACE_P(it, slot) TC_TRACE_RAW(trole, it, slot)
+#else
+#define TC_TRACE(role, it, slot) TC_TRACE_RAW(role, it, slot)
+#define TC_TRACE_P(it, slot) TC_TRACE_RAW(1, it, slot)
+#endif
 #else
 #define TC_TRACE(role, it, slot) do { } while (0)
+#define TC_TRACE_P(it, slot) do { } while (0)
 #endif
 
 struct TcSmem {
@@ -366,7 +441,7 @@ __host__ __device__ inline TcSmem tc_smem_layout_impl(const Layout& l, int epi, 
   s.state = o; o += (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;
   s.il = o;    o += (uint32_t)round_up(l.dp4, 4) * 4;
   o = (o + 15) / 16 * 16;
-  s.bars = o;  o += 32 * 8;
+  s.bars = o;  o += 40 * 8;
   s.total = o;
   return s;
 }
@@ -581,20 +656,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sl.bars);
   uint64_t* b_full = bars;             // [8]
   uint64_t* b_empty = bars + 8;        // [8]
-  uint64_t* a_full = bars + 16;        // [4]
-  uint64_t* a_empty = bars + 20;       // [4]
-  uint64_t* d_full = bars + 24;        // [2]
-  uint64_t* d_empty = bars + 26;       // [2]
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* a_full = bars + 16;        // [8]: [stage] or [stage][k-step]
+  uint64_t* a_empty = bars + 24;       // [8]
+  uint64_t* d_full = bars + 32;        // [2]
+  uint64_t* d_empty = bars + 34;       // [2]
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 36);
 
   constexpr int TKB = C::TKB;
-  constexpr int TC_FPW = TKB / (TC_NPROD / 4);  // features per producer warp per block
+  constexpr bool GEN = (DP == 0);           // generic d: x in shared memory, table blocks streamed
+  // Producer groups (register-x BF16x3 kernel): group g evaluates the blocks with it % GRP == g, each of its
+  // TC_NPROD / GRP warps GRP sub-blocks of TC_FPW features in turn.  One a_empty wait / tcgen05.wait::st /
+  // a_full arrive then serves GRP x TC_FPW features per warp, and the groups are in different phases of a
+  // block (one waits or stores while the other keeps the XU pipe busy).
+  constexpr int GRP = (BF && !GEN) ? PSBAX_TC_GROUPS : 1;
+  static_assert(GRP == 1 || GRP == 2, "one or two producer groups");
+  constexpr int TC_FPW = TKB / (TC_NPROD / 4);  // features per producer warp per sub-block
+  // Deferred hand-over (small d, x in registers): the four producer warps of a scheduler do identical work and
+  // stay in lock step (clock trace: starts within ~500 cycles of each other), so a serial wait / store /
+  // wait::st / fence / arrive tail at the end of every block (~640 of ~1900 cycles) leaves the XU pipe idle for
+  // all of them at once.  Instead the a_empty probe is issued at the top of the block, and the previous block's
+  // wait::st + arrive after the first feature group of the current one, when the stores have long completed.
+  constexpr bool DEFER = PSBAX_TC_DEFER && !GEN && DP < 12;
   // feature blocks: nkb_r blocks of TKB rows (RFF / linear rows; every block in the 3xTF32 engine),
   // then (BF16x3 engine) nkb_k exact-kernel blocks of TKB / 2 rows contracted in 3xTF32
   const int nkb_r = lay.nkb_r;
   const int nkb = lay.nkb_r + lay.nkb_k;
   constexpr int KF = TKB / 2;               // rows of an exact-kernel block
-  constexpr bool GEN = (DP == 0);           // generic d: x in shared memory, table blocks streamed
   constexpr int OSC = (DP + 1 + 3) / 4 * 4; // row stride of the table for this DP (compile time)
   const int OS = GEN ? lay.OS : OSC;
   constexpr int NSB = C::NSB;
@@ -617,7 +704,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   if (tid == 0) {
     // generic d: the producers read the streamed table block, so they release the stage too
     for (int i = 0; i < NSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], GEN ? 1 + TC_NPROD : 1); }
-    for (int i = 0; i < C::NSA; ++i) { mbar_init(&a_full[i], TC_NPROD); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::NSA; ++i) { mbar_init(&a_full[i], TC_NPROD / GRP); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], TC_NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -633,7 +720,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
 
-  if (warp == TC_WARP_LOAD) {
+  if (PSBAX_EXP_FREERUN && !(warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_NPROD)) {
+  } else if (warp == TC_WARP_LOAD) {
     // ================= B loader =================
     const uint8_t* gB = reinterpret_cast<const uint8_t*>(a.pack + lay.off_tc) +
                         (size_t)blockIdx.y * nkb * C::BBYTES;
@@ -649,8 +737,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           const bool kblk = BF && kb >= nkb_r;
           const uint32_t fb = kblk ? ftbytes / 2 : ftbytes;
           const size_t frow = kblk ? (size_t)lay.kk0 + (size_t)(kb - nkb_r) * KF : (size_t)kb * TKB;
+#if PSBAX_EXP_NOCOPY  // what-if build (wrong results): the operand stream is not read at all
+          mbar_arrive_expect_tx(&b_full[bs], (GEN ? fb : 0u));
+#else
           mbar_arrive_expect_tx(&b_full[bs], C::BBYTES + (GEN ? fb : 0u));
           bulk_g2s(sB + bs * STAGE, gB + (size_t)kb * C::BBYTES, C::BBYTES, &b_full[bs]);
+#endif
           if constexpr (GEN)
             bulk_g2s(sB + bs * STAGE + C::BBYTES, gFT + frow * OS * 4, fb, &b_full[bs]);
         }
@@ -668,7 +760,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     bool ready = false;
     for (int pass = t0; pass < t1; ++pass, ++tl) {
       const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
-      mbar_wait(&d_empty[buf], dph ^ 1);  // all lanes poll: the single issuer warp stays converged
+      mbar_wait_all<PSBAX_TC_ISSUER_HINT>(&d_empty[buf], dph ^ 1);  // all lanes poll: the single issuer warp stays converged
       __syncwarp();
       tc_fence_after();
       const uint32_t d_addr = tmem + TC_COL_D + buf * (TC_TILES * TN);
@@ -676,68 +768,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         const uint32_t bs = it % NSB;
         const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
         TC_TRACE(0, it, 0);
+        const uint32_t a_base = tmem + TC_COL_A + as * (TC_TILES * C::ACT);
+        const uint32_t bbase = smem_u32(sB + bs * STAGE);
         if (!ready) {
-          mbar_wait(&b_full[bs], (it / NSB) & 1);
-          mbar_wait(&a_full[as], aph);
+          mbar_wait_all<PSBAX_TC_ISSUER_HINT>(&b_full[bs], (it / NSB) & 1);
+          mbar_wait_all<PSBAX_TC_ISSUER_HINT>(&a_full[as], aph);
           __syncwarp();
         }
         TC_TRACE(0, it, 1);
         tc_fence_after();
-        const uint32_t a_base = tmem + TC_COL_A + as * (TC_TILES * C::ACT);
-        const uint32_t bbase = smem_u32(sB + bs * STAGE);
-#pragma unroll
-        for (int t = 0; t < TC_TILES; ++t) {
-          if (t == TC_TILES - 1) {  // probe block it + 1 while tile 0's MMAs are queued
-            const uint32_t nit = it + 1;
-            const bool ok = mbar_test(&a_full[nit % C::NSA], (nit / C::NSA) & 1) &&
-                            mbar_test(&b_full[nit % NSB], (nit / NSB) & 1);
-            ready = __all_sync(0xffffffffu, ok) != 0;
-          }
+        // Issue order: k-step major, and inside a k-step the two row tiles alternate MMA by MMA, so that
+        // consecutive MMAs accumulate into DIFFERENT tensor-memory tiles.  Twelve MMAs in a row into one
+        // accumulator (the round-1 order: tile 0's whole block, then tile 1's) ran at about half the tensor
+        // pipe's rate: same-box A/B 8.23 -> 7.84 ms at C2.  Per accumulator the order of additions is unchanged.
+        if (elect_one()) {
+          const uint32_t d0 = d_addr, d1 = d_addr + TN;
           if (BF && kb >= nkb_r) {
             // exact-kernel block: KF features as TF32 hi | lo (A columns [0, KF) | [KF, 2 KF)), K = 8 per MMA
-            if (elect_one()) {
-              constexpr uint32_t IDESC_K = umma_idesc_tf32(TN);
-              constexpr uint32_t SBO_K = KF * 4 * 8, SPLIT2_K = 8 * SBO_K;
+            constexpr uint32_t IDESC_K = umma_idesc_tf32(TN);
+            constexpr uint32_t SBO_K = KF * 4 * 8, SPLIT2_K = 8 * SBO_K;
 #pragma unroll
-              for (int ks = 0; ks < KF / 8; ++ks) {
-                const uint64_t b1 = umma_desc_kmajor(bbase + ks * 256, 128, SBO_K);
-                const uint64_t b2 = umma_desc_kmajor(bbase + SPLIT2_K + ks * 256, 128, SBO_K);
-                const uint32_t a1 = a_base + t * C::ACT + ks * 8, a2 = a1 + C::ACT / 2;
-                const uint32_t d = d_addr + t * TN;
-                tc_mma_ts(d, a1, b1, IDESC_K, (kb | ks) ? 1u : 0u);
-                tc_mma_ts(d, a1, b2, IDESC_K, 1u);
-                tc_mma_ts(d, a2, b1, IDESC_K, 1u);
-              }
-              if (t == TC_TILES - 1) {
-                tc_commit(&b_empty[bs]);
-                tc_commit(&a_empty[as]);
-                if (kb == nkb - 1) tc_commit(&d_full[buf]);
-              }
+            for (int ks = 0; ks < KF / 8; ++ks) {
+              const uint64_t b1 = umma_desc_kmajor(bbase + ks * 256, 128, SBO_K);
+              const uint64_t b2 = umma_desc_kmajor(bbase + SPLIT2_K + ks * 256, 128, SBO_K);
+              const uint32_t a10 = a_base + ks * 8, a20 = a10 + C::ACT / 2;
+              const uint32_t a11 = a10 + C::ACT, a21 = a11 + C::ACT / 2;
+              tc_mma_ts(d0, a10, b1, IDESC_K, (kb | ks) ? 1u : 0u);
+              tc_mma_ts(d1, a11, b1, IDESC_K, (kb | ks) ? 1u : 0u);
+              tc_mma_ts(d0, a10, b2, IDESC_K, 1u);
+              tc_mma_ts(d1, a11, b2, IDESC_K, 1u);
+              tc_mma_ts(d0, a20, b1, IDESC_K, 1u);
+              tc_mma_ts(d1, a21, b1, IDESC_K, 1u);
             }
-          } else if (elect_one()) {
+          } else {
 #pragma unroll
             for (int ks = 0; ks < C::KSTEPS; ++ks) {
               const uint64_t b1 = umma_desc_kmajor(bbase + ks * C::B_KSTEP, 128, C::B_SBO);
               const uint64_t b2 = umma_desc_kmajor(bbase + C::B_SPLIT2 + ks * C::B_KSTEP, 128, C::B_SBO);
-              const uint32_t a1 = a_base + t * C::ACT + ks * C::A_KSTEP, a2 = a1 + C::A_SPLIT2;
-              const uint32_t d = d_addr + t * TN;
+              const uint32_t a10 = a_base + ks * C::A_KSTEP, a20 = a10 + C::A_SPLIT2;
+              const uint32_t a11 = a10 + C::ACT, a21 = a11 + C::A_SPLIT2;
               if constexpr (BF) {
-                tc_mma_ts_bf16(d, a1, b1, IDESC, (kb | ks) ? 1u : 0u);
-                tc_mma_ts_bf16(d, a1, b2, IDESC, 1u);
-                tc_mma_ts_bf16(d, a2, b1, IDESC, 1u);
+#if !PSBAX_EXP_NOMMA  // what-if build (wrong results): the issuer only commits
+                tc_mma_ts_bf16(d0, a10, b1, IDESC, (kb | ks) ? 1u : 0u);
+                tc_mma_ts_bf16(d1, a11, b1, IDESC, (kb | ks) ? 1u : 0u);
+                tc_mma_ts_bf16(d0, a10, b2, IDESC, 1u);
+                tc_mma_ts_bf16(d1, a11, b2, IDESC, 1u);
+                tc_mma_ts_bf16(d0, a20, b1, IDESC, 1u);
+                tc_mma_ts_bf16(d1, a21, b1, IDESC, 1u);
+#endif
               } else {
-                tc_mma_ts(d, a1, b1, IDESC, (kb | ks) ? 1u : 0u);
-                tc_mma_ts(d, a1, b2, IDESC, 1u);
-                tc_mma_ts(d, a2, b1, IDESC, 1u);
+                tc_mma_ts(d0, a10, b1, IDESC, (kb | ks) ? 1u : 0u);
+                tc_mma_ts(d1, a11, b1, IDESC, (kb | ks) ? 1u : 0u);
+                tc_mma_ts(d0, a10, b2, IDESC, 1u);
+                tc_mma_ts(d1, a11, b2, IDESC, 1u);
+                tc_mma_ts(d0, a20, b1, IDESC, 1u);
+                tc_mma_ts(d1, a21, b1, IDESC, 1u);
               }
             }
-            if (t == TC_TILES - 1) {  // release the stages (and publish the accumulators)
-              tc_commit(&b_empty[bs]);
-              tc_commit(&a_empty[as]);
-              if (kb == nkb - 1) tc_commit(&d_full[buf]);
-            }
           }
-          __syncwarp();
+          // release the stages (and publish the accumulators)
+          tc_commit(&b_empty[bs]);
+          tc_commit(&a_empty[as]);
+          if (kb == nkb - 1) tc_commit(&d_full[buf]);
+        }
+        __syncwarp();
+        {  // probe block it + 1 while this block's MMAs are queued
+          const uint32_t nit = it + 1;
+          const bool ok = mbar_test(&a_full[nit % C::NSA], (nit / C::NSA) & 1) &&
+                          mbar_test(&b_full[nit % NSB], (nit / NSB) & 1);
+          ready = __all_sync(0xffffffffu, ok) != 0;
         }
         TC_TRACE(0, it, 2);
       }
@@ -745,11 +844,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   } else if (warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_NPROD) {
     // ================= producers =================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int h = (warp - TC_PROD_WARP0) >> 2;    // which 8 of the block's 32 features
+    const int hh = (warp - TC_PROD_WARP0) >> 2;   // 0 .. TC_NPROD / 4 - 1
+    const uint32_t grp = (uint32_t)hh % GRP;      // producer group: blocks with it % GRP == grp
+    const int hw = hh / GRP;                      // this warp's slot in its group
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+#if defined(PSBAX_TC_TRACE) && PSBAX_TC_TRACE == 2
+    const bool tracer = (q == 0 && lane == 0);
+    const int trole = hh;
+    (void)trole;
+#else
     const bool tracer = (warp == TC_PROD_WARP0 && lane == 0);
+#endif
     (void)tracer;
     uint32_t it = 0;
+#if PSBAX_TC_STAGGER > 0
+    // The four producer warps of a scheduler (same lane quarter, feature slices 0..3) do identical work and
+    // would run in lock step: all in the XU-bound math phase together, then all in the latency-bound
+    // wait / tcgen05.st / arrive phase together with the XU pipe idle.  A one-time start offset puts them in
+    // different phases; nothing re-aligns them while the A ring has slack.
+    if (hh > 0) {
+      const long long t_end = clock64() + (long long)hh * PSBAX_TC_STAGGER;
+      while (clock64() < t_end) { }
+      __syncwarp();
+    }
+#endif
+    constexpr uint32_t NOPEND = 0xffffffffu;
+    uint32_t pend = NOPEND;  // A stage whose stores are in flight and whose a_full arrive is still owed
+    auto flush = [&]() {
+      if (pend != NOPEND) {
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0 && !PSBAX_EXP_FREERUN) mbar_arrive(&a_full[pend]);
+        pend = NOPEND;
+      }
+    };
+    uint64_t xnext[GEN ? 1 : DP];
+    (void)xnext;
+    auto load_rows = [&](int pass, uint64_t (&xr)[GEN ? 1 : DP]) {
+      const long long row0 = (long long)pass * TC_TILES * TM + q * 32 + lane, row1 = row0 + TM;
+#pragma unroll
+      for (int i = 0; i < (GEN ? 0 : DP); ++i) {
+        const float x0 = (row0 < a.N && i < lay.d) ? load_x(a, row0, i) : 0.f;
+        const float x1 = (row1 < a.N && i < lay.d) ? load_x(a, row1, i) : 0.f;
+        xr[i] = pack2(x0, x1);
+      }
+    };
     for (int pass = t0; pass < t1; ++pass) {
       static_assert(TC_TILES == 2, "the packed-FMA producers pair the two row tiles of a pass");
       uint64_t xp[GEN ? 1 : DP];  // (x of tile 0, x of tile 1) per dimension
@@ -770,26 +910,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           sX[lay.d * TM * TC_TILES + idx] = 0.f;
         asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
       } else {
-        const long long row0 = (long long)pass * TC_TILES * TM + q * 32 + lane, row1 = row0 + TM;
+        if constexpr (PSBAX_TC_XPREFETCH && DP <= 4) {
+        // the rows of this pass were requested a pass ago (their DRAM latency would otherwise sit at the head
+        // of every pass: ~1 k of ~33 k cycles); request the next pass's now
+        if (pass == t0) load_rows(pass, xnext);
 #pragma unroll
-        for (int i = 0; i < DP; ++i) {
-          const float x0 = (row0 < a.N && i < lay.d) ? load_x(a, row0, i) : 0.f;
-          const float x1 = (row1 < a.N && i < lay.d) ? load_x(a, row1, i) : 0.f;
-          xp[i] = pack2(x0, x1);
+        for (int i = 0; i < DP; ++i) xp[i] = xnext[i];
+        if (pass + 1 < t1) load_rows(pass + 1, xnext);
+        } else {
+        load_rows(pass, xp);
         }
       }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
+        if (GRP > 1 && it % GRP != grp) continue;  // the other group's block
         const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
+        if (tracer) TC_TRACE_P(it, 0);
+        const uint32_t bs = it % NSB;
+        const bool kblk = BF && kb >= nkb_r;
+        const uint32_t ab = as;
+        bool a_ready = false;
+        if constexpr (DEFER) a_ready = PSBAX_EXP_FREERUN || PSBAX_EXP_NOAEMPTY || __all_sync(0xffffffffu, mbar_test(&a_empty[ab], aph ^ 1)) != 0;
+#pragma unroll 1
+        for (int sb = 0; sb < GRP; ++sb) {
+        const int h = hw * GRP + sb;  // which TC_FPW features of the block
         const int kbase0 = kb * TKB + h * TC_FPW;
-        if (tracer) TC_TRACE(1, it, 0);
         constexpr int NG = TC_FPW / 8;
         // EARLY: wait for the stage after the first 8-feature group and store every group at once
         // (lower register pressure: large DP / generic d); otherwise compute all groups before the
         // wait, so that its latency hides behind the math (measured better for small d)
         constexpr bool EARLY = GEN || DP >= 12;
         uint32_t s1[NG][TC_TILES][C::WCOLS], s2[NG][TC_TILES][C::WCOLS];
-        const uint32_t bs = it % NSB;
-        const bool kblk = BF && kb >= nkb_r;
         if (kblk) {
           // ---- exact-kernel block of the BF16x3 engine: KF features, TF32 hi | lo operands ----
           // x in registers: KF = 32, 8 features per warp; generic d: KF = 16, 4 features per warp.
@@ -851,8 +1001,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
               }
             }
           }
-          mbar_wait_hybrid_sleep<PSBAX_AEMPTY_HINT>(&a_empty[as], aph ^ 1, lane);
-          tc_fence_after();
+          if (sb == 0) {
+            if constexpr (DEFER) flush();
+            if (!a_ready) mbar_wait_hybrid_sleep<PSBAX_AEMPTY_HINT>(&a_empty[ab], aph ^ 1, lane);
+            tc_fence_after();
+          }
 #pragma unroll
           for (int t = 0; t < TC_TILES; ++t) {
             const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + h * KW;
@@ -943,14 +1096,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float w[OSC];
+#if PSBAX_EXP_NOLDS  // what-if build (wrong results): table entries made up in registers, no shared-memory loads
+#pragma unroll
+              for (int i = 0; i < OSC; ++i) w[i] = __uint_as_float(0x3f000000u + (uint32_t)(kbase + j) * 64u + i * 7u);
+#else
               load_row<OSC>(ft + j * OSC, w);
+#endif
               uint64_t arg = pack2(w[DP], w[DP]);
 #pragma unroll
               for (int i = 0; i < DP; ++i) arg = ffma2(xp[i], pack2(w[i], w[i]), arg);
               float a0, a1;
               unpack2(arg, a0, a1);
+#if PSBAX_EXP_NOCOS  // what-if build (wrong results): no MUFU
+              v[0][j] = a0 * 0.37f;
+              v[1][j] = a1 * 0.37f;
+#else
               v[0][j] = lin ? a0 : __cosf(a0);
               v[1][j] = lin ? a1 : __cosf(a1);
+#endif
             }
           } else {
             float r2[TC_TILES][8];
@@ -979,6 +1142,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             for (int c = 0; c < 4; ++c) {  // column c packs features 2c (low half) and 2c + 1 (high half)
               const uint32_t p1a = cvt_bf16x2(v[0][2 * c + 1], v[0][2 * c]);
               const uint32_t p1b = cvt_bf16x2(v[1][2 * c + 1], v[1][2 * c]);
+#if PSBAX_SPLIT_FHFMA
+              float a0, a1, b0, b1;  // residuals: a = feature 2c, b = feature 2c + 1; 0 / 1 = tile
+              bf16_residual2(p1a, v[0][2 * c], v[0][2 * c + 1], a0, b0);
+              bf16_residual2(p1b, v[1][2 * c], v[1][2 * c + 1], a1, b1);
+#else
               const uint64_t ra = ffma2(pack2(__uint_as_float(p1a << 16), __uint_as_float(p1b << 16)),
                                         pack2(-1.0f, -1.0f), pack2(v[0][2 * c], v[1][2 * c]));
               const uint64_t rb = ffma2(pack2(__uint_as_float(p1a & 0xffff0000u), __uint_as_float(p1b & 0xffff0000u)),
@@ -986,6 +1154,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
               float a0, a1, b0, b1;
               unpack2(ra, a0, a1);
               unpack2(rb, b0, b1);
+#endif
               s1[g][0][c] = p1a;
               s1[g][1][c] = p1b;
               s2[g][0][c] = cvt_bf16x2(b0, a0);
@@ -998,11 +1167,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
 #pragma unroll
               for (int c = 0; c < 4; ++c) {  // column c packs features 2c (low half) and 2c + 1 (high half)
                 const uint32_t p1 = cvt_bf16x2(v[t][2 * c + 1], v[t][2 * c]);
+                float r0, r1;
+#if PSBAX_SPLIT_FHFMA
+                bf16_residual2(p1, v[t][2 * c], v[t][2 * c + 1], r0, r1);
+#else
                 // residual pair (v - bf16(v)) as one packed FMA: (-1) * x1 + v
                 const uint64_t rr = ffma2(pack2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u)),
                                           pack2(-1.0f, -1.0f), pack2(v[t][2 * c], v[t][2 * c + 1]));
-                float r0, r1;
                 unpack2(rr, r0, r1);
+#endif
                 s1[g][t][c] = p1;
                 s2[g][t][c] = cvt_bf16x2(r1, r0);
               }
@@ -1016,10 +1189,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             }
           }
           }
-          if (EARLY ? (g == 0) : (g == NG - 1)) {
-            if (tracer) TC_TRACE(1, it, 1);
-            mbar_wait_hybrid_sleep<PSBAX_AEMPTY_HINT>(&a_empty[as], aph ^ 1, lane);
-            if (tracer) TC_TRACE(1, it, 2);
+          if constexpr (DEFER) {
+            if (sb == 0 && g == 0) flush();
+          }
+          if (sb == 0 && (EARLY ? (g == 0) : (g == NG - 1))) {
+            if (tracer) TC_TRACE_P(it, 1);
+            if (!a_ready) mbar_wait_hybrid_sleep<PSBAX_AEMPTY_HINT>(&a_empty[ab], aph ^ 1, lane);
+            if (tracer) TC_TRACE_P(it, 2);
             tc_fence_after();
           }
           if constexpr (!EARLY && BF && NG == 2) {
@@ -1033,7 +1209,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
                                         s1[1][t][0], s1[1][t][1], s1[1][t][2], s1[1][t][3],
                                         s2[0][t][0], s2[0][t][1], s2[0][t][2], s2[0][t][3],
                                         s2[1][t][0], s2[1][t][1], s2[1][t][2], s2[1][t][3]};
+#if PSBAX_EXP_NOSTTM  // what-if build (wrong results): values consumed by a dummy, no tensor-memory store
+                uint32_t x = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x ^= u[i];
+                if (x == 0x12345678u) sIl[0] = 1.f;
+#else
                 tc_st16(lane_addr + col, u);
+#endif
               }
             }
           } else if (EARLY || g == NG - 1) {
@@ -1061,18 +1244,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           for (int g = 0; g < NG; ++g) group(std::false_type{}, g);
         }
         }  // !kblk
+        }  // sub-blocks
         if constexpr (GEN) {  // done reading the streamed table block
           __syncwarp();
           if (lane == 0) mbar_arrive(&b_empty[bs]);
         }
-        tc_wait_st();
-        if (tracer) TC_TRACE(1, it, 3);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[as]);
-        if (tracer) TC_TRACE(1, it, 4);
+        if constexpr (DEFER) {
+          pend = ab;
+          if (tracer) TC_TRACE_P(it, 3);
+          if (tracer) TC_TRACE_P(it, 4);
+        } else {
+          tc_wait_st();
+          if (tracer) TC_TRACE_P(it, 3);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[ab]);
+          if (tracer) TC_TRACE_P(it, 4);
+        }
       }
     }
+    flush();
   } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_NEPI) {
     // ================= epilogue =================
     const int q = warp & 3;
@@ -1108,7 +1299,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 2);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
-        if (tile < a.ntiles) {
+        if (tile < a.ntiles && !PSBAX_EXP_NOEPI) {
           if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg<TC_NEPI>(a, sOut, ls, tile * TM, s0, etid);
           else epilogue_tile<EPI, TC_NEPI>(a, sOut, e, tile * TM, s0, etid);
         }

@@ -436,20 +436,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
       TC_TRACE(0, jt, 4);
       if (elect_one()) {
         const uint64_t oh0 = dO0 + (uint64_t)(bs * stage16), ol0 = oh0 + osplit16;
-        // exact-kernel blocks have no projection: only the barrier protocol runs
-#pragma unroll
-        for (int t = 0; t < (kblk ? 0 : TILES); ++t) {
-          const uint32_t dz = tmem + M::Z + (zb * TILES + t) * 32;
-          const uint32_t xh = tmem + M::X + (t * 2) * 32, xl = xh + 32;
-          tc_mma_ts(dz, xh, oh0, IDESC_P, 0u);
-          tc_mma_ts(dz, xh, ol0, IDESC_P, 1u);
-          tc_mma_ts(dz, xl, oh0, IDESC_P, 1u);
+        // exact-kernel blocks have no projection: only the barrier protocol runs.  Consecutive MMAs alternate
+        // between the row tiles' Z accumulators (a run of MMAs into one accumulator is serialised by the
+        // tensor pipe: sp_tensor.cuh, issue order); per accumulator the order of additions is unchanged.
+        if (!kblk) {
 #pragma unroll 1
-          for (int ks = 1; ks < nks; ++ks) {
+          for (int ks = 0; ks < nks; ++ks) {
             const uint64_t oh = oh0 + (uint64_t)(ks * 16), ol = ol0 + (uint64_t)(ks * 16);
-            tc_mma_ts(dz, xh + ks * 8, oh, IDESC_P, 1u);
-            tc_mma_ts(dz, xh + ks * 8, ol, IDESC_P, 1u);
-            tc_mma_ts(dz, xl + ks * 8, oh, IDESC_P, 1u);
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+              for (int t = 0; t < TILES; ++t) {
+                const uint32_t dz = tmem + M::Z + (zb * TILES + t) * 32;
+                const uint32_t xh = tmem + M::X + (t * 2) * 32 + ks * 8, xl = xh + 32;
+                tc_mma_ts(dz, pr == 2 ? xl : xh, pr == 1 ? ol : oh, IDESC_P, (ks | pr) ? 1u : 0u);
+              }
           }
         }
         tc_commit(&z_full[jt % ZB]);
@@ -487,35 +488,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           constexpr uint32_t IDESC_K = umma_idesc_tf32(TN);
           constexpr uint32_t SBO_K = KF * 4 * 8, SPLIT2_K = 8 * SBO_K;
           const uint64_t k10 = umma_desc_kmajor(smem_u32(sB), 128, SBO_K) + (uint64_t)(bs * stage16);
+          // k-step major, then the three split products, the (chunk, tile) accumulators innermost: consecutive
+          // MMAs go to different accumulators; per accumulator the order of additions is unchanged
+#pragma unroll
+          for (int ks = 0; ks < KF / 8; ++ks)
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr)
 #pragma unroll 1
-          for (int c = 0; c < nch; ++c)
+              for (int c = 0; c < nch; ++c)
 #pragma unroll
-            for (int t = 0; t < TILES; ++t)
-#pragma unroll
-              for (int ks = 0; ks < KF / 8; ++ks) {
-                const uint64_t b1 = k10 + (uint64_t)(c * (TP_WBYTES >> 4) + ks * 16);
-                const uint64_t b2 = b1 + (uint64_t)(SPLIT2_K >> 4);
-                const uint32_t a1 = tmem + M::A + (as * TILES + t) * 32 + ks * 8, a2 = a1 + 16;
-                const uint32_t dd = tmem + M::D + (c * TILES + t) * TN;
-                tc_mma_ts(dd, a1, b1, IDESC_K, (kb | ks) ? 1u : 0u);
-                tc_mma_ts(dd, a1, b2, IDESC_K, 1u);
-                tc_mma_ts(dd, a2, b1, IDESC_K, 1u);
-              }
+                for (int t = 0; t < TILES; ++t) {
+                  const uint64_t b1 = k10 + (uint64_t)(c * (TP_WBYTES >> 4) + ks * 16);
+                  const uint64_t b2 = b1 + (uint64_t)(SPLIT2_K >> 4);
+                  const uint32_t a1 = tmem + M::A + (as * TILES + t) * 32 + ks * 8, a2 = a1 + 16;
+                  const uint32_t dd = tmem + M::D + (c * TILES + t) * TN;
+                  tc_mma_ts(dd, pr == 2 ? a2 : a1, pr == 1 ? b2 : b1, IDESC_K, (kb | ks | pr) ? 1u : 0u);
+                }
         } else {
+#pragma unroll
+          for (int ks = 0; ks < C::KSTEPS; ++ks)
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr)
 #pragma unroll 1
-          for (int c = 0; c < nch; ++c)
+              for (int c = 0; c < nch; ++c)
 #pragma unroll
-            for (int t = 0; t < TILES; ++t)
-#pragma unroll
-              for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                const uint64_t b1 = b10 + (uint64_t)(c * (TP_WBYTES >> 4) + ks * (C::B_KSTEP >> 4));
-                const uint64_t b2 = b1 + (uint64_t)(C::B_SPLIT2 >> 4);
-                const uint32_t a1 = tmem + M::A + (as * TILES + t) * 32 + ks * 8, a2 = a1 + 16;
-                const uint32_t dd = tmem + M::D + (c * TILES + t) * TN;
-                tc_mma_ts_bf16(dd, a1, b1, IDESC_C, (kb | ks) ? 1u : 0u);
-                tc_mma_ts_bf16(dd, a1, b2, IDESC_C, 1u);
-                tc_mma_ts_bf16(dd, a2, b1, IDESC_C, 1u);
-              }
+                for (int t = 0; t < TILES; ++t) {
+                  const uint64_t b1 = b10 + (uint64_t)(c * (TP_WBYTES >> 4) + ks * (C::B_KSTEP >> 4));
+                  const uint64_t b2 = b1 + (uint64_t)(C::B_SPLIT2 >> 4);
+                  const uint32_t a1 = tmem + M::A + (as * TILES + t) * 32 + ks * 8, a2 = a1 + 16;
+                  const uint32_t dd = tmem + M::D + (c * TILES + t) * TN;
+                  tc_mma_ts_bf16(dd, pr == 2 ? a2 : a1, pr == 1 ? b2 : b1, IDESC_C, (kb | ks | pr) ? 1u : 0u);
+                }
         }
         tc_commit(&a_empty[as]);
         tc_commit(&b_empty[bs]);
@@ -651,10 +654,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const uint32_t p1 = cvt_bf16x2(v[t][2 * c + 1], v[t][2 * c]);
+                float r0, r1;
+#if PSBAX_SPLIT_FHFMA
+                bf16_residual2(p1, v[t][2 * c], v[t][2 * c + 1], r0, r1);
+#else
                 const uint64_t rr = ffma2(pack2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u)),
                                           pack2(-1.0f, -1.0f), pack2(v[t][2 * c], v[t][2 * c + 1]));
-                float r0, r1;
                 unpack2(rr, r0, r1);
+#endif
                 s1[t][c] = p1;
                 s2[t][c] = cvt_bf16x2(r1, r0);
               }
