@@ -226,7 +226,8 @@ def roofline(wl, engine, kern_s, rows, with_mask, traffic=None, kernel_name=""):
     Lf, n, Sx, d = w["L"], w["n"], w["S"], w["d"]
     pk = load_peaks()
     bf16 = float(pk.get("bf16_tflops", 1590.0)) * 1e12
-    hbm = float(pk.get("hbm_gbps", 6500.0)) * 1e9
+    hbm = float(pk.get("hbm_gbs", pk.get("hbm_gbps", 6500.0))) * 1e9
+    bf16_sus = float(pk.get("bf16_tflops_sustained", 0.0)) * 1e12
     which = "MEASURED_PEAKS.json (bf16 burst, hbm copy)" if pk else "fallback 1590 TF bf16 / 6500 GB/s (B200_PROFILING.md)"
     clk, sms = 1.965e9, 148
     split = 6.0 if engine == "tensor_tf32x3" else 3.0
@@ -250,7 +251,12 @@ def roofline(wl, engine, kern_s, rows, with_mask, traffic=None, kernel_name=""):
     frac = t_roof / kern_s
     peak, unit = {"tensor": (p_tensor / 1e12, "TFLOP/s"), "mufu": (p_mufu / 1e12, "Tops/s"),
                   "ffma": (p_ffma / 1e12, "TFLOP/s"), "hbm": (hbm / 1e9, "GB/s")}[bound]
-    return {"bound": bound, "achieved": frac * peak, "peak": peak, "unit": unit, "frac": frac, "traffic": traffic,
+    # the same fraction against the SUSTAINED tensor peak (cuBLAS bf16 back to back for 4 s: the board's power cap
+    # holds it ~15 % under the burst figure).  `frac` stays against the burst peak; a run whose `clocks.reasons`
+    # shows sw_power_cap (the c2 kernel does, after ~8 back-to-back steps) is in the sustained regime.
+    frac_sus = (frac * bf16 / bf16_sus) if (bound == "tensor" and bf16_sus > 0) else None
+    return {"bound": bound, "achieved": frac * peak, "peak": peak, "unit": unit, "frac": frac,
+            "frac_vs_sustained_peak": frac_sus, "traffic": traffic,
             "kernel": kernel_name, "kernel_ms": 1e3 * kern_s, "roofline_ms": 1e3 * t_roof,
             "pipes_ms": {k: 1e3 * v * rows for k, v in pipes.items()}, "mapping": best,
             "algorithmic": {"contraction_flop_per_candidate": contract, "mufu_ops_per_candidate": sfu,
@@ -537,13 +543,23 @@ def run_ours(args):
         step = lambda: paths.subset_select(X, etas, w["k"])  # noqa: E731
         launches, kname, with_mask = 2, "evaluate (values) kernel; greedy subset-select kernel timed beside it", False
 
-    for _ in range(Wm):
-        res = step()
-    ctx.sync_all()
+    # clock ramp: a fresh box hands over the GPU in an idle power state and three 8 ms steps do not lift it
+    # (seen once in round 2: 49 ms per step for the first steps, 7.8 ms right after); untimed, before the W
+    # warm-up steps the contract asks for
+    # The clock sampler must be LIVE before the timed region: nvidia-smi's start-up (NVML attach on a box without
+    # the persistence daemon) stalls the GPU once for 50-80 ms, and with a fixed 0.3 s head start that stall landed
+    # inside the second timed step (round 2: 82 ms among 7.5 ms steps).  The wait is idle (no extra GPU work: the
+    # W warm-up steps the contract asks for are the only warm-up, so the first timed steps run at burst clocks
+    # and the later ones under the board's power cap; `ms_first_last` shows the drift).
     clocks = Clocks(ctx.local)
     if rank == 0:
         clocks.start()
-        time.sleep(0.3)
+        t_live = time.time()
+        while clocks.proc is not None and len(clocks.rows) < 3 and time.time() - t_live < 8.0:
+            time.sleep(0.05)
+    for _ in range(Wm):
+        res = step()
+    ctx.sync_all()
     w0 = time.time()
     span, kern_ms, wall, res = timed_steps(ctx, step, K, flush)
     if os.environ.get("PSBAX_BENCH_DEBUG"):
@@ -624,6 +640,7 @@ def run_ours(args):
             "roofline": roofline(wl, eng, kern_s, N, with_mask, traffic, kname),
             "cpu_baseline": cpu, "cpu_best_effort": best, "clocks": clk,
             "wall_ms_per_step": 1e3 * wall / K,
+            "ms_first_last": [float(np.mean(kern_ms[:3])), float(np.mean(kern_ms[-3:]))],  # rank 0: power-cap drift
             "param_draw_ms": {"cold": draw_ms[0], "warm": draw_ms[1]},
             "check": chk,
         }

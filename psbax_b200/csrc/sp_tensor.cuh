@@ -55,6 +55,12 @@ constexpr int TC_MAX_S = 1 << 20;  // any S: processed in chunks of 64 samples
 #ifndef PSBAX_TC_XPREFETCH
 #define PSBAX_TC_XPREFETCH 0  // (measured: no gain; costs registers) register-x kernels: the next pass's candidate rows are loaded during the current pass
 #endif
+#ifndef PSBAX_TC_MMA_B4
+#define PSBAX_TC_MMA_B4 0
+#endif
+#ifndef PSBAX_TC_FT3
+#define PSBAX_TC_FT3 1  // d <= 2: a second, dense copy of the feature table (12-byte rows): six LDS.128 per eight features
+#endif
 #ifndef PSBAX_TC_DEFER
 #define PSBAX_TC_DEFER 0  // (measured: no gain, 8.24 -> 8.30 ms) register-x kernels: a block's tcgen05.wait::st + a_full arrive are issued inside the next block's math
 #endif
@@ -418,7 +424,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int N) {
 struct TcSmem {
   // byte offsets into dynamic shared memory.  `b`: ring of NSB stages of `stage` bytes: the B
   // image and, for generic d, the 32-row block of the feature table behind it.
-  uint32_t b, stage, nsb, ft, x, out, state, il, bars, total;
+  uint32_t b, stage, nsb, ft, ft3, x, out, state, il, bars, total;
   bool generic;
 };
 __host__ __device__ inline TcSmem tc_smem_layout_impl(const Layout& l, int epi, int k, bool generic) {
@@ -436,6 +442,7 @@ __host__ __device__ inline TcSmem tc_smem_layout_impl(const Layout& l, int epi, 
   uint32_t o = 0;
   s.b = o;     o += s.nsb * s.stage;
   s.ft = o;    o += generic ? 0u : kp * l.OS * 4;                         // resident table (small d)
+  s.ft3 = o;   o += (PSBAX_TC_FT3 && !generic && l.dp4 == 2) ? (kp * 12u + 15u) / 16u * 16u : 0u;  // dense (omega_1, omega_2, b) rows
   s.x = o;     o += generic ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u;   // x tile [i][row] of (tile 0, tile 1) pairs
   s.out = o;   o += TN * OUT_LD * 4;
   s.state = o; o += (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;
@@ -650,6 +657,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   const TcSmem sl = tc_smem_layout(lay, EPI, a.k);
   uint8_t* sB = smem + sl.b;
   float* sFT = reinterpret_cast<float*>(smem + sl.ft);
+  constexpr bool FT3 = PSBAX_TC_FT3 && DP == 2;
+  float* sFT3 = reinterpret_cast<float*>(smem + sl.ft3);
+  (void)sFT3;
   float* sOut = reinterpret_cast<float*>(smem + sl.out);
   float* sState = reinterpret_cast<float*>(smem + sl.state);
   float* sIl = reinterpret_cast<float*>(smem + sl.il);
@@ -700,6 +710,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
       for (int i = tid; i < lay.Kp * OS / 4; i += TC_THREADS) reinterpret_cast<float4*>(sFT)[i] = __ldg(src + i);
     }
     for (int i = tid; i < round_up(lay.dp4, 4); i += TC_THREADS) sIl[i] = __ldg(a.pack + lay.off_invls + i);
+    if constexpr (FT3) {
+      const float* src = a.pack + lay.off_ft;
+      for (int i = tid; i < lay.Kp * 3; i += TC_THREADS) sFT3[i] = __ldg(src + (i / 3) * OS + (i % 3));
+    }
   }
   if (tid == 0) {
     // generic d: the producers read the streamed table block, so they release the stage too
@@ -809,12 +823,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
               const uint32_t a11 = a10 + C::ACT, a21 = a11 + C::A_SPLIT2;
               if constexpr (BF) {
 #if !PSBAX_EXP_NOMMA  // what-if build (wrong results): the issuer only commits
+#if PSBAX_TC_MMA_B4  // the four products that read B split 1 back to back
+                tc_mma_ts_bf16(d0, a10, b1, IDESC, (kb | ks) ? 1u : 0u);
+                tc_mma_ts_bf16(d1, a11, b1, IDESC, (kb | ks) ? 1u : 0u);
+                tc_mma_ts_bf16(d0, a20, b1, IDESC, 1u);
+                tc_mma_ts_bf16(d1, a21, b1, IDESC, 1u);
+                tc_mma_ts_bf16(d0, a10, b2, IDESC, 1u);
+                tc_mma_ts_bf16(d1, a11, b2, IDESC, 1u);
+#else
                 tc_mma_ts_bf16(d0, a10, b1, IDESC, (kb | ks) ? 1u : 0u);
                 tc_mma_ts_bf16(d1, a11, b1, IDESC, (kb | ks) ? 1u : 0u);
                 tc_mma_ts_bf16(d0, a10, b2, IDESC, 1u);
                 tc_mma_ts_bf16(d1, a11, b2, IDESC, 1u);
                 tc_mma_ts_bf16(d0, a20, b1, IDESC, 1u);
                 tc_mma_ts_bf16(d1, a21, b1, IDESC, 1u);
+#endif
 #endif
               } else {
                 tc_mma_ts(d0, a10, b1, IDESC, (kb | ks) ? 1u : 0u);
@@ -1091,6 +1114,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             } else {
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t) kernel_profile8(acc[t], v[t], lay.kernel);
+            }
+          } else if (FT3 && PURE) {
+            // dense rows: 24 floats = six 16-byte loads for the group's eight features
+            float f[24];
+            const float4* t4 = reinterpret_cast<const float4*>(sFT3 + kbase * 3);
+#pragma unroll
+            for (int u4 = 0; u4 < 6; ++u4) {
+              const float4 qv = t4[u4];
+              f[4 * u4] = qv.x; f[4 * u4 + 1] = qv.y; f[4 * u4 + 2] = qv.z; f[4 * u4 + 3] = qv.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint64_t arg = pack2(f[3 * j + 2], f[3 * j + 2]);
+              arg = ffma2(xp[0], pack2(f[3 * j], f[3 * j]), arg);
+              arg = ffma2(xp[DP - 1], pack2(f[3 * j + 1], f[3 * j + 1]), arg);
+              float a0, a1;
+              unpack2(arg, a0, a1);
+              v[0][j] = __cosf(a0);
+              v[1][j] = __cosf(a1);
             }
           } else if (PURE || kbase < lay.Lp_ft) {
 #pragma unroll
