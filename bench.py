@@ -768,13 +768,16 @@ def leg_strong(ctx, paths, tau, K):
 
     for _ in range(3):
         r = step()
-    span, _ms, _wall, r = timed_steps(ctx, step, K, flush=False)
-    (span,) = ctx.max_over_ranks([span])
+    span, ms, _wall, r = timed_steps(ctx, step, K, flush=False)
+    span, med = ctx.max_over_ranks([span, float(np.median(ms)) / 1e3])
     cnt = r.count.clone()
     if world > 1:
         ctx.dist.all_reduce(cnt)
+    # the median is reported beside the mean: this leg runs after the host-buffer legs, and one of its steps
+    # sometimes carries a ~45 ms host-side stall (pinned buffers of the previous leg being released)
     return {"candidates_total": Ntot, "samples": paths.S, "scaling": "strong", "ms_per_step": 1e3 * span / K,
-            "evals_per_s": Ntot * paths.S * K / span, "count_s0_total": int(cnt[0]), "ranks": world}
+            "ms_per_step_median": 1e3 * med, "evals_per_s": Ntot * paths.S * K / span,
+            "count_s0_total": int(cnt[0]), "ranks": world}
 
 
 DTYPES = {"simt": "f32 (FFMA + MUFU)",
