@@ -61,6 +61,9 @@ constexpr int TC_MAX_S = 1 << 20;  // any S: processed in chunks of 64 samples
 #ifndef PSBAX_TC_FT3
 #define PSBAX_TC_FT3 1  // d <= 2: a second, dense copy of the feature table (12-byte rows): six LDS.128 per eight features
 #endif
+#ifndef PSBAX_TC_SINGLE_D
+#define PSBAX_TC_SINGLE_D 0  // (measured: no change, 7.58 vs 7.59 ms) register-x kernels: one accumulator set (drained to shared memory at the pass boundary), three A stages
+#endif
 #ifndef PSBAX_TC_DEFER
 #define PSBAX_TC_DEFER 0  // (measured: no gain, 8.24 -> 8.30 ms) register-x kernels: a block's tcgen05.wait::st + a_full arrive are issued inside the next block's math
 #endif
@@ -444,7 +447,7 @@ __host__ __device__ inline TcSmem tc_smem_layout_impl(const Layout& l, int epi, 
   s.ft = o;    o += generic ? 0u : kp * l.OS * 4;                         // resident table (small d)
   s.ft3 = o;   o += (PSBAX_TC_FT3 && !generic && l.dp4 == 2) ? (kp * 12u + 15u) / 16u * 16u : 0u;  // dense (omega_1, omega_2, b) rows
   s.x = o;     o += generic ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u;   // x tile [i][row] of (tile 0, tile 1) pairs
-  s.out = o;   o += TN * OUT_LD * 4;
+  s.out = o;   o += TN * OUT_LD * 4 * ((PSBAX_TC_SINGLE_D && !generic) ? TC_TILES : 1);  // one staging tile per row tile
   s.state = o; o += (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;
   s.il = o;    o += (uint32_t)round_up(l.dp4, 4) * 4;
   o = (o + 15) / 16 * 16;
@@ -692,6 +695,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   const int nkb_r = lay.nkb_r;
   const int nkb = lay.nkb_r + lay.nkb_k;
   constexpr int KF = TKB / 2;               // rows of an exact-kernel block
+  // Tensor-memory map.  Generic d: D[buf][tile] double-buffered at 0..255, A ring at 256..511.  x in registers
+  // (PSBAX_TC_SINGLE_D): ONE accumulator set D[tile] at 0..127 and the A ring at 128..511 — three 64-feature
+  // stages instead of two.  The producers of a scheduler run in lock step and the two-stage ring was what every
+  // attempt to de-phase them ran out of; the price is that the next pass's first MMAs wait until the epilogue
+  // has copied both accumulator tiles to shared memory (~1.5 k cycles per ~30 k-cycle pass, covered by the ring).
+  constexpr bool SD = PSBAX_TC_SINGLE_D && !GEN;
+  constexpr uint32_t COL_A = SD ? (uint32_t)(TC_TILES * TN) : (uint32_t)TC_COL_A;
+  constexpr int NSA_ = SD ? (int)((TC_TMEM_COLS - COL_A) / (TC_TILES * C::ACT)) : C::NSA;
+  static_assert(NSA_ >= 2 && NSA_ <= 8, "A ring depth");
   constexpr int OSC = (DP + 1 + 3) / 4 * 4; // row stride of the table for this DP (compile time)
   const int OS = GEN ? lay.OS : OSC;
   constexpr int NSB = C::NSB;
@@ -718,7 +730,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   if (tid == 0) {
     // generic d: the producers read the streamed table block, so they release the stage too
     for (int i = 0; i < NSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], GEN ? 1 + TC_NPROD : 1); }
-    for (int i = 0; i < C::NSA; ++i) { mbar_init(&a_full[i], TC_NPROD / GRP); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NSA_; ++i) { mbar_init(&a_full[i], TC_NPROD / GRP); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], TC_NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -773,16 +785,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     uint32_t it = 0, tl = 0;
     bool ready = false;
     for (int pass = t0; pass < t1; ++pass, ++tl) {
-      const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
+      const uint32_t buf = SD ? 0u : (tl & 1), dph = SD ? (tl & 1) : ((tl >> 1) & 1);
       mbar_wait_all<PSBAX_TC_ISSUER_HINT>(&d_empty[buf], dph ^ 1);  // all lanes poll: the single issuer warp stays converged
       __syncwarp();
       tc_fence_after();
       const uint32_t d_addr = tmem + TC_COL_D + buf * (TC_TILES * TN);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t bs = it % NSB;
-        const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
+        const uint32_t as = it % NSA_, aph = (it / NSA_) & 1;
         TC_TRACE(0, it, 0);
-        const uint32_t a_base = tmem + TC_COL_A + as * (TC_TILES * C::ACT);
+        const uint32_t a_base = tmem + COL_A + as * (TC_TILES * C::ACT);
         const uint32_t bbase = smem_u32(sB + bs * STAGE);
         if (!ready) {
           mbar_wait_all<PSBAX_TC_ISSUER_HINT>(&b_full[bs], (it / NSB) & 1);
@@ -857,7 +869,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         __syncwarp();
         {  // probe block it + 1 while this block's MMAs are queued
           const uint32_t nit = it + 1;
-          const bool ok = mbar_test(&a_full[nit % C::NSA], (nit / C::NSA) & 1) &&
+          const bool ok = mbar_test(&a_full[nit % NSA_], (nit / NSA_) & 1) &&
                           mbar_test(&b_full[nit % NSB], (nit / NSB) & 1);
           ready = __all_sync(0xffffffffu, ok) != 0;
         }
@@ -946,7 +958,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
       }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         if (GRP > 1 && it % GRP != grp) continue;  // the other group's block
-        const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
+        const uint32_t as = it % NSA_, aph = (it / NSA_) & 1;
         if (tracer) TC_TRACE_P(it, 0);
         const uint32_t bs = it % NSB;
         const bool kblk = BF && kb >= nkb_r;
@@ -1031,7 +1043,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           }
 #pragma unroll
           for (int t = 0; t < TC_TILES; ++t) {
-            const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + h * KW;
+            const uint32_t col = COL_A + (as * TC_TILES + t) * C::ACT + h * KW;
             if constexpr (GEN) {
               tc_st4(lane_addr + col, khi[t]);
               tc_st4(lane_addr + col + C::ACT / 2, klo[t]);
@@ -1246,7 +1258,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t) {
                 static_assert(C::INTERLEAVED && NG * C::WCOLS == C::KCOLS, "one k-step per producer warp");
-                const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + h * C::A_KSTEP;
+                const uint32_t col = COL_A + (as * TC_TILES + t) * C::ACT + h * C::A_KSTEP;
                 const uint32_t u[16] = {s1[0][t][0], s1[0][t][1], s1[0][t][2], s1[0][t][3],
                                         s1[1][t][0], s1[1][t][1], s1[1][t][2], s1[1][t][3],
                                         s2[0][t][0], s2[0][t][1], s2[0][t][2], s2[0][t][3],
@@ -1266,7 +1278,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             for (int gg = EARLY ? g : 0; gg <= g; ++gg)
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t) {
-                const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT +
+                const uint32_t col = COL_A + (as * TC_TILES + t) * C::ACT +
                                      (C::INTERLEAVED ? h * C::A_KSTEP + gg * C::WCOLS : (h * NG + gg) * C::WCOLS);
                 if constexpr (BF) {
                   tc_st4(lane_addr + col, s1[gg][t]);
@@ -1315,12 +1327,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     ls.init();
     uint32_t tl = 0;
     for (int pass = t0; pass < t1; ++pass, ++tl) {
-      const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
+      const uint32_t buf = SD ? 0u : (tl & 1), dph = SD ? (tl & 1) : ((tl >> 1) & 1);
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 0);
       mbar_wait_hybrid_sleep<20000>(&d_full[buf], dph, lane);
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 1);
       tc_fence_after();
       const int r = q * 32 + lane;
+      if constexpr (SD) {
+        // single accumulator set: both tiles leave tensor memory first (one staging tile each), the accumulators
+        // are released, and only then do the reductions run
+#pragma unroll 1
+        for (int t = 0; t < TC_TILES; ++t) {
+          if (pass * TC_TILES + t < a.ntiles) {
+            float* so = sOut + t * (TN * OUT_LD);
+#pragma unroll 1
+            for (int c = 0; c < TN / 16; ++c) {
+              uint32_t u[16];
+              tc_ld16(lane_addr + TC_COL_D + t * TN + c * 16, u);
+              tc_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) so[(c * 16 + j) * OUT_LD + r] = __uint_as_float(u[j]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d_empty[0]);
+        if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 2);
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
+#pragma unroll 1
+        for (int t = 0; t < TC_TILES; ++t) {
+          const int tile = pass * TC_TILES + t;
+          if (tile < a.ntiles && !PSBAX_EXP_NOEPI) {
+            const float* so = sOut + t * (TN * OUT_LD);
+            if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg<TC_NEPI>(a, so, ls, tile * TM, s0, etid);
+            else epilogue_tile<EPI, TC_NEPI>(a, so, e, tile * TM, s0, etid);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");  // staging tiles free for the next pass
+      } else {
 #pragma unroll 1
       for (int t = 0; t < TC_TILES; ++t) {
         const int tile = pass * TC_TILES + t;
@@ -1346,6 +1391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           else epilogue_tile<EPI, TC_NEPI>(a, sOut, e, tile * TM, s0, etid);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
+      }
       }
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 3);
     }

@@ -494,10 +494,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           for (int ks = 0; ks < KF / 8; ++ks)
 #pragma unroll
             for (int pr = 0; pr < 3; ++pr)
-#pragma unroll 1
-              for (int c = 0; c < nch; ++c)
+#pragma unroll
+              for (int c = 0; c < NCH; ++c)
 #pragma unroll
                 for (int t = 0; t < TILES; ++t) {
+                  if (c >= nch) continue;  // (the last CTA column may have fewer chunks)
                   const uint64_t b1 = k10 + (uint64_t)(c * (TP_WBYTES >> 4) + ks * 16);
                   const uint64_t b2 = b1 + (uint64_t)(SPLIT2_K >> 4);
                   const uint32_t a1 = tmem + M::A + (as * TILES + t) * 32 + ks * 8, a2 = a1 + 16;
@@ -509,10 +510,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tensor_proj(const __grid_cons
           for (int ks = 0; ks < C::KSTEPS; ++ks)
 #pragma unroll
             for (int pr = 0; pr < 3; ++pr)
-#pragma unroll 1
-              for (int c = 0; c < nch; ++c)
+#pragma unroll
+              for (int c = 0; c < NCH; ++c)
 #pragma unroll
                 for (int t = 0; t < TILES; ++t) {
+                  if (c >= nch) continue;
                   const uint64_t b1 = b10 + (uint64_t)(c * (TP_WBYTES >> 4) + ks * (C::B_KSTEP >> 4));
                   const uint64_t b2 = b1 + (uint64_t)(C::B_SPLIT2 >> 4);
                   const uint32_t a1 = tmem + M::A + (as * TILES + t) * 32 + ks * 8, a2 = a1 + 16;
