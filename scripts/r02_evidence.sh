@@ -20,7 +20,7 @@ ncu --set full --clock-control none --import-source on -k regex:k_shared_tensor 
     python bench.py --workload c2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02f/ncu_full_c2.log 2>&1
 for w in c3 c5; do
   python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02f/plain2_$w.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:k_tensor_proj -s 4 -c 1 -f -o gpurun_out/r02f/full_$w \
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:k_tensor_proj<\(int\)[12]' -s 3 -c 1 -f -o gpurun_out/r02f/full_$w \
       python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02f/ncu_full_$w.log 2>&1
 done
 python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/r02f/plain2_c4.log 2>&1 &&
