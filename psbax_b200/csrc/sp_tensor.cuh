@@ -590,6 +590,11 @@ __device__ __forceinline__ void epilogue_levelset_reg_impl(const KArgs& a, const
   const int warp = tid >> 5, lane = tid & 31;
   const long long N = a.N;
   const bool wr = a.mask != nullptr && lane < TM / 32 && (FULL || (long long)row0 + lane * 32 < N);
+  // Everything about the mask store that does not depend on the sample is formed once per tile: lane g < 4 owns
+  // the word of row group g, the samples of this warp are mask_ld words apart (the pointer walks).  Under the
+  // board's power cap the kernel is energy-bound and this epilogue was 13 % of its executed instructions.
+  unsigned int* mp = a.mask + ((long long)(s0 + warp * SPW) * a.mask_ld + (row0 >> 5) + lane);
+  const int nvalid = a.lay.S - (s0 + warp * SPW);  // samples of this warp that exist (padding samples evaluate to c0)
   unsigned int pool = 0u;  // lane g < 4: OR over this warp's samples of row group g's word
 #pragma unroll
   for (int q = 0; q < SPW; ++q) {
@@ -602,15 +607,16 @@ __device__ __forceinline__ void epilogue_levelset_reg_impl(const KArgs& a, const
       const bool valid = FULL || row < N;  // FULL: every row of the tile exists (all tiles but the last)
       const float y = fmaf(sOut[sl * OUT_LD + r], a.ystd, a.c0);
       const unsigned int word = __ballot_sync(0xffffffffu, valid && (y > a.tau));
-      st.cnt[q] += __popc(word);
       if (lane == g) mine = word;
       // rows only grow for a given lane, so a tie never replaces the earlier (smaller) index
       if (valid && y > st.bv[q]) { st.bv[q] = y; st.bi[q] = row; }
     }
-    if (s0 + sl < a.lay.S) {  // (padding samples evaluate to the constant c0: never part of the pool)
-      if (wr) a.mask[(long long)(s0 + sl) * a.mask_ld + (row0 >> 5) + lane] = mine;
+    st.cnt[q] += __popc(mine);  // per lane (lanes 0..3 hold the four words); summed over the lanes at the flush
+    if (q < nvalid) {
+      if (wr) *mp = mine;
       pool |= mine;
     }
+    mp += a.mask_ld;
   }
   if (a.pooled != nullptr && lane < TM / 32 && pool != 0u) atomicOr(a.pooled + (row0 >> 5) + lane, pool);
 }
@@ -630,6 +636,9 @@ __device__ __forceinline__ void epilogue_levelset_reg_flush(const KArgs& a, LsRe
   for (int q = 0; q < SPW; ++q) {
     float bv = st.bv[q];
     int bi = st.bi[q];
+    unsigned int cnt = st.cnt[q];  // lanes 0..3 counted one row group each
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
@@ -638,7 +647,7 @@ __device__ __forceinline__ void epilogue_levelset_reg_flush(const KArgs& a, LsRe
     }
     if (lane == 0) {
       const size_t o = (size_t)blockIdx.x * a.lay.Sp + s0 + warp * SPW + q;
-      a.p_cnt[o] = st.cnt[q];
+      a.p_cnt[o] = cnt;
       a.p_max[o] = bv;
       a.p_arg[o] = bi;
     }
