@@ -64,6 +64,9 @@ constexpr int TC_MAX_S = 1 << 20;  // any S: processed in chunks of 64 samples
 #ifndef PSBAX_TC_SINGLE_D
 #define PSBAX_TC_SINGLE_D 0  // (measured: no change, 7.58 vs 7.59 ms) register-x kernels: one accumulator set (drained to shared memory at the pass boundary), three A stages
 #endif
+#ifndef PSBAX_TC_SLEEP_NS
+#define PSBAX_TC_SLEEP_NS 2000  // real sleeps (ns) between the fallback probes of the roles with slack: loader (b_empty), epilogue (d_full)
+#endif
 #ifndef PSBAX_TC_DEFER
 #define PSBAX_TC_DEFER 0  // (measured: no gain, 8.24 -> 8.30 ms) register-x kernels: a block's tcgen05.wait::st + a_full arrive are issued inside the next block's math
 #endif
@@ -272,6 +275,20 @@ __device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
     }
   } else {
     mbar_wait(bar, parity);
+  }
+}
+// warp-level wait for roles with slack: one converged probe; on failure lane 0 sleeps NS ns between probes
+template <int NS>
+__device__ __forceinline__ void mbar_wait_hybrid_nanosleep(uint64_t* bar, uint32_t parity, int lane) {
+  if (!__all_sync(0xffffffffu, mbar_test(bar, parity))) {
+    if (lane == 0) {
+      uint32_t spins = 0;
+      while (!mbar_test(bar, parity)) {
+        __nanosleep(NS);
+        if (++spins > (1u << 24)) asm volatile("trap;");
+      }
+    }
+    __syncwarp();
   }
 }
 #ifndef PSBAX_AEMPTY_HINT
@@ -766,7 +783,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     for (int pass = t0; pass < t1; ++pass) {
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t bs = it % NSB, ph = (it / NSB) & 1;
-        mbar_wait_hybrid(&b_empty[bs], ph ^ 1, lane);
+        if constexpr (PSBAX_TC_SLEEP_NS > 0) mbar_wait_hybrid_nanosleep<PSBAX_TC_SLEEP_NS / 4>(&b_empty[bs], ph ^ 1, lane);
+        else mbar_wait_hybrid(&b_empty[bs], ph ^ 1, lane);
         if (elect_one()) {
           // table rows of the block (generic d): TKB rows from kb * TKB, or the KF rows of an exact-kernel block
           const bool kblk = BF && kb >= nkb_r;
@@ -1338,7 +1356,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     for (int pass = t0; pass < t1; ++pass, ++tl) {
       const uint32_t buf = SD ? 0u : (tl & 1), dph = SD ? (tl & 1) : ((tl >> 1) & 1);
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 0);
-      mbar_wait_hybrid_sleep<20000>(&d_full[buf], dph, lane);
+      if constexpr (PSBAX_TC_SLEEP_NS > 0) mbar_wait_hybrid_nanosleep<PSBAX_TC_SLEEP_NS>(&d_full[buf], dph, lane);
+      else mbar_wait_hybrid_sleep<20000>(&d_full[buf], dph, lane);
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 1);
       tc_fence_after();
       const int r = q * 32 + lane;
