@@ -46,32 +46,11 @@ constexpr int TC_MAX_S = 1 << 20;  // any S: processed in chunks of 64 samples
 #ifndef PSBAX_TC_NPROD
 #define PSBAX_TC_NPROD 16
 #endif
-#ifndef PSBAX_TC_GROUPS
-#define PSBAX_TC_GROUPS 1  // producer groups of the register-x BF16x3 kernel taking alternate blocks (1: every warp on every block)
-#endif
-#ifndef PSBAX_TC_ISSUER_HINT
-#define PSBAX_TC_ISSUER_HINT 0  // suspend-time hint (ns) of the MMA issuer's and the loader's barrier waits; 0 = plain try_wait
-#endif
-#ifndef PSBAX_TC_XPREFETCH
-#define PSBAX_TC_XPREFETCH 0  // (measured: no gain; costs registers) register-x kernels: the next pass's candidate rows are loaded during the current pass
-#endif
-#ifndef PSBAX_TC_MMA_B4
-#define PSBAX_TC_MMA_B4 0
-#endif
 #ifndef PSBAX_TC_FT3
 #define PSBAX_TC_FT3 1  // d <= 2: a second, dense copy of the feature table (12-byte rows): six LDS.128 per eight features
 #endif
-#ifndef PSBAX_TC_SINGLE_D
-#define PSBAX_TC_SINGLE_D 0  // (measured: no change, 7.58 vs 7.59 ms) register-x kernels: one accumulator set (drained to shared memory at the pass boundary), three A stages
-#endif
 #ifndef PSBAX_TC_SLEEP_NS
 #define PSBAX_TC_SLEEP_NS 2000  // real sleeps (ns) between the fallback probes of the roles with slack: loader (b_empty), epilogue (d_full)
-#endif
-#ifndef PSBAX_TC_DEFER
-#define PSBAX_TC_DEFER 0  // (measured: no gain, 8.24 -> 8.30 ms) register-x kernels: a block's tcgen05.wait::st + a_full arrive are issued inside the next block's math
-#endif
-#ifndef PSBAX_TC_STAGGER
-#define PSBAX_TC_STAGGER 0  // cycles of start offset between the producer warps of one scheduler
 #endif
 #ifndef PSBAX_EXP_NOLDS
 #define PSBAX_EXP_NOLDS 0
@@ -265,18 +244,6 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
-// all lanes wait (the warp stays converged) with a suspend-time hint: fewer probes from a warp that only waits
-template <int NS>
-__device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) {
-  if constexpr (NS > 0) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait_hint(bar, parity, NS)) {
-      if (++spins > (1u << 24)) asm volatile("trap;");
-    }
-  } else {
-    mbar_wait(bar, parity);
-  }
-}
 // warp-level wait for roles with slack: one converged probe; on failure lane 0 sleeps NS ns between probes
 template <int NS>
 __device__ __forceinline__ void mbar_wait_hybrid_nanosleep(uint64_t* bar, uint32_t parity, int lane) {
@@ -464,7 +431,7 @@ __host__ __device__ inline TcSmem tc_smem_layout_impl(const Layout& l, int epi, 
   s.ft = o;    o += generic ? 0u : kp * l.OS * 4;                         // resident table (small d)
   s.ft3 = o;   o += (PSBAX_TC_FT3 && !generic && l.dp4 == 2) ? (kp * 12u + 15u) / 16u * 16u : 0u;  // dense (omega_1, omega_2, b) rows
   s.x = o;     o += generic ? (uint32_t)TC_TILES * l.dp4 * TM * 4 : 0u;   // x tile [i][row] of (tile 0, tile 1) pairs
-  s.out = o;   o += TN * OUT_LD * 4 * ((PSBAX_TC_SINGLE_D && !generic) ? TC_TILES : 1);  // one staging tile per row tile
+  s.out = o;   o += TN * OUT_LD * 4;
   s.state = o; o += (uint32_t)round_up((int)epi_smem_floats(epi, k), 4) * 4;
   s.il = o;    o += (uint32_t)round_up(l.dp4, 4) * 4;
   o = (o + 15) / 16 * 16;
@@ -703,33 +670,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
 
   constexpr int TKB = C::TKB;
   constexpr bool GEN = (DP == 0);           // generic d: x in shared memory, table blocks streamed
-  // Producer groups (register-x BF16x3 kernel): group g evaluates the blocks with it % GRP == g, each of its
-  // TC_NPROD / GRP warps GRP sub-blocks of TC_FPW features in turn.  One a_empty wait / tcgen05.wait::st /
-  // a_full arrive then serves GRP x TC_FPW features per warp, and the groups are in different phases of a
-  // block (one waits or stores while the other keeps the XU pipe busy).
-  constexpr int GRP = (BF && !GEN) ? PSBAX_TC_GROUPS : 1;
-  static_assert(GRP == 1 || GRP == 2, "one or two producer groups");
-  constexpr int TC_FPW = TKB / (TC_NPROD / 4);  // features per producer warp per sub-block
-  // Deferred hand-over (small d, x in registers): the four producer warps of a scheduler do identical work and
-  // stay in lock step (clock trace: starts within ~500 cycles of each other), so a serial wait / store /
-  // wait::st / fence / arrive tail at the end of every block (~640 of ~1900 cycles) leaves the XU pipe idle for
-  // all of them at once.  Instead the a_empty probe is issued at the top of the block, and the previous block's
-  // wait::st + arrive after the first feature group of the current one, when the stores have long completed.
-  constexpr bool DEFER = PSBAX_TC_DEFER && !GEN && DP < 12;
+  constexpr int TC_FPW = TKB / (TC_NPROD / 4);  // features per producer warp per block
   // feature blocks: nkb_r blocks of TKB rows (RFF / linear rows; every block in the 3xTF32 engine),
   // then (BF16x3 engine) nkb_k exact-kernel blocks of TKB / 2 rows contracted in 3xTF32
   const int nkb_r = lay.nkb_r;
   const int nkb = lay.nkb_r + lay.nkb_k;
   constexpr int KF = TKB / 2;               // rows of an exact-kernel block
-  // Tensor-memory map.  Generic d: D[buf][tile] double-buffered at 0..255, A ring at 256..511.  x in registers
-  // (PSBAX_TC_SINGLE_D): ONE accumulator set D[tile] at 0..127 and the A ring at 128..511 — three 64-feature
-  // stages instead of two.  The producers of a scheduler run in lock step and the two-stage ring was what every
-  // attempt to de-phase them ran out of; the price is that the next pass's first MMAs wait until the epilogue
-  // has copied both accumulator tiles to shared memory (~1.5 k cycles per ~30 k-cycle pass, covered by the ring).
-  constexpr bool SD = PSBAX_TC_SINGLE_D && !GEN;
-  constexpr uint32_t COL_A = SD ? (uint32_t)(TC_TILES * TN) : (uint32_t)TC_COL_A;
-  constexpr int NSA_ = SD ? (int)((TC_TMEM_COLS - COL_A) / (TC_TILES * C::ACT)) : C::NSA;
-  static_assert(NSA_ >= 2 && NSA_ <= 8, "A ring depth");
   constexpr int OSC = (DP + 1 + 3) / 4 * 4; // row stride of the table for this DP (compile time)
   const int OS = GEN ? lay.OS : OSC;
   constexpr int NSB = C::NSB;
@@ -756,7 +702,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   if (tid == 0) {
     // generic d: the producers read the streamed table block, so they release the stage too
     for (int i = 0; i < NSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], GEN ? 1 + TC_NPROD : 1); }
-    for (int i = 0; i < NSA_; ++i) { mbar_init(&a_full[i], TC_NPROD / GRP); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::NSA; ++i) { mbar_init(&a_full[i], TC_NPROD); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], TC_NEPI); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -812,20 +758,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     uint32_t it = 0, tl = 0;
     bool ready = false;
     for (int pass = t0; pass < t1; ++pass, ++tl) {
-      const uint32_t buf = SD ? 0u : (tl & 1), dph = SD ? (tl & 1) : ((tl >> 1) & 1);
-      mbar_wait_all<PSBAX_TC_ISSUER_HINT>(&d_empty[buf], dph ^ 1);  // all lanes poll: the single issuer warp stays converged
+      const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
+      mbar_wait(&d_empty[buf], dph ^ 1);  // all lanes poll: the single issuer warp stays converged
       __syncwarp();
       tc_fence_after();
       const uint32_t d_addr = tmem + TC_COL_D + buf * (TC_TILES * TN);
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const uint32_t bs = it % NSB;
-        const uint32_t as = it % NSA_, aph = (it / NSA_) & 1;
+        const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
         TC_TRACE(0, it, 0);
-        const uint32_t a_base = tmem + COL_A + as * (TC_TILES * C::ACT);
+        const uint32_t a_base = tmem + TC_COL_A + as * (TC_TILES * C::ACT);
         const uint32_t bbase = smem_u32(sB + bs * STAGE);
         if (!ready) {
-          mbar_wait_all<PSBAX_TC_ISSUER_HINT>(&b_full[bs], (it / NSB) & 1);
-          mbar_wait_all<PSBAX_TC_ISSUER_HINT>(&a_full[as], aph);
+          mbar_wait(&b_full[bs], (it / NSB) & 1);
+          mbar_wait(&a_full[as], aph);
           __syncwarp();
         }
         TC_TRACE(0, it, 1);
@@ -862,21 +808,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
               const uint32_t a11 = a10 + C::ACT, a21 = a11 + C::A_SPLIT2;
               if constexpr (BF) {
 #if !PSBAX_EXP_NOMMA  // what-if build (wrong results): the issuer only commits
-#if PSBAX_TC_MMA_B4  // the four products that read B split 1 back to back
-                tc_mma_ts_bf16(d0, a10, b1, IDESC, (kb | ks) ? 1u : 0u);
-                tc_mma_ts_bf16(d1, a11, b1, IDESC, (kb | ks) ? 1u : 0u);
-                tc_mma_ts_bf16(d0, a20, b1, IDESC, 1u);
-                tc_mma_ts_bf16(d1, a21, b1, IDESC, 1u);
-                tc_mma_ts_bf16(d0, a10, b2, IDESC, 1u);
-                tc_mma_ts_bf16(d1, a11, b2, IDESC, 1u);
-#else
                 tc_mma_ts_bf16(d0, a10, b1, IDESC, (kb | ks) ? 1u : 0u);
                 tc_mma_ts_bf16(d1, a11, b1, IDESC, (kb | ks) ? 1u : 0u);
                 tc_mma_ts_bf16(d0, a10, b2, IDESC, 1u);
                 tc_mma_ts_bf16(d1, a11, b2, IDESC, 1u);
                 tc_mma_ts_bf16(d0, a20, b1, IDESC, 1u);
                 tc_mma_ts_bf16(d1, a21, b1, IDESC, 1u);
-#endif
 #endif
               } else {
                 tc_mma_ts(d0, a10, b1, IDESC, (kb | ks) ? 1u : 0u);
@@ -896,7 +833,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
         __syncwarp();
         {  // probe block it + 1 while this block's MMAs are queued
           const uint32_t nit = it + 1;
-          const bool ok = mbar_test(&a_full[nit % NSA_], (nit / NSA_) & 1) &&
+          const bool ok = mbar_test(&a_full[nit % C::NSA], (nit / C::NSA) & 1) &&
                           mbar_test(&b_full[nit % NSB], (nit / NSB) & 1);
           ready = __all_sync(0xffffffffu, ok) != 0;
         }
@@ -906,43 +843,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
   } else if (warp >= TC_PROD_WARP0 && warp < TC_PROD_WARP0 + TC_NPROD) {
     // ================= producers =================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int hh = (warp - TC_PROD_WARP0) >> 2;   // 0 .. TC_NPROD / 4 - 1
-    const uint32_t grp = (uint32_t)hh % GRP;      // producer group: blocks with it % GRP == grp
-    const int hw = hh / GRP;                      // this warp's slot in its group
+    const int h = (warp - TC_PROD_WARP0) >> 2;    // which TC_FPW features of every block: 0 .. TC_NPROD / 4 - 1
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
 #if defined(PSBAX_TC_TRACE) && PSBAX_TC_TRACE == 2
     const bool tracer = (q == 0 && lane == 0);
-    const int trole = hh;
+    const int trole = h;
     (void)trole;
 #else
     const bool tracer = (warp == TC_PROD_WARP0 && lane == 0);
 #endif
     (void)tracer;
     uint32_t it = 0;
-#if PSBAX_TC_STAGGER > 0
-    // The four producer warps of a scheduler (same lane quarter, feature slices 0..3) do identical work and
-    // would run in lock step: all in the XU-bound math phase together, then all in the latency-bound
-    // wait / tcgen05.st / arrive phase together with the XU pipe idle.  A one-time start offset puts them in
-    // different phases; nothing re-aligns them while the A ring has slack.
-    if (hh > 0) {
-      const long long t_end = clock64() + (long long)hh * PSBAX_TC_STAGGER;
-      while (clock64() < t_end) { }
-      __syncwarp();
-    }
-#endif
-    constexpr uint32_t NOPEND = 0xffffffffu;
-    uint32_t pend = NOPEND;  // A stage whose stores are in flight and whose a_full arrive is still owed
-    auto flush = [&]() {
-      if (pend != NOPEND) {
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0 && !PSBAX_EXP_FREERUN) mbar_arrive(&a_full[pend]);
-        pend = NOPEND;
-      }
-    };
-    uint64_t xnext[GEN ? 1 : DP];
-    (void)xnext;
     auto load_rows = [&](int pass, uint64_t (&xr)[GEN ? 1 : DP]) {
       const long long row0 = (long long)pass * TC_TILES * TM + q * 32 + lane, row1 = row0 + TM;
 #pragma unroll
@@ -972,29 +883,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           sX[lay.d * TM * TC_TILES + idx] = 0.f;
         asm volatile("bar.sync 2, %0;" ::"n"(PT) : "memory");
       } else {
-        if constexpr (PSBAX_TC_XPREFETCH && DP <= 4) {
-        // the rows of this pass were requested a pass ago (their DRAM latency would otherwise sit at the head
-        // of every pass: ~1 k of ~33 k cycles); request the next pass's now
-        if (pass == t0) load_rows(pass, xnext);
-#pragma unroll
-        for (int i = 0; i < DP; ++i) xp[i] = xnext[i];
-        if (pass + 1 < t1) load_rows(pass + 1, xnext);
-        } else {
         load_rows(pass, xp);
-        }
       }
       for (int kb = 0; kb < nkb; ++kb, ++it) {
-        if (GRP > 1 && it % GRP != grp) continue;  // the other group's block
-        const uint32_t as = it % NSA_, aph = (it / NSA_) & 1;
+        const uint32_t as = it % C::NSA, aph = (it / C::NSA) & 1;
         if (tracer) TC_TRACE_P(it, 0);
         const uint32_t bs = it % NSB;
         const bool kblk = BF && kb >= nkb_r;
-        const uint32_t ab = as;
-        bool a_ready = false;
-        if constexpr (DEFER) a_ready = PSBAX_EXP_FREERUN || PSBAX_EXP_NOAEMPTY || __all_sync(0xffffffffu, mbar_test(&a_empty[ab], aph ^ 1)) != 0;
-#pragma unroll 1
-        for (int sb = 0; sb < GRP; ++sb) {
-        const int h = hw * GRP + sb;  // which TC_FPW features of the block
+        constexpr bool a_ready = PSBAX_EXP_FREERUN || PSBAX_EXP_NOAEMPTY;  // what-if builds never wait for the stage
         const int kbase0 = kb * TKB + h * TC_FPW;
         constexpr int NG = TC_FPW / 8;
         // EARLY: wait for the stage after the first 8-feature group and store every group at once
@@ -1063,14 +959,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
               }
             }
           }
-          if (sb == 0) {
-            if constexpr (DEFER) flush();
-            if (!a_ready) mbar_wait_hybrid_sleep<PSBAX_AEMPTY_HINT>(&a_empty[ab], aph ^ 1, lane);
-            tc_fence_after();
-          }
+          if (!a_ready) mbar_wait_hybrid_sleep<PSBAX_AEMPTY_HINT>(&a_empty[as], aph ^ 1, lane);
+          tc_fence_after();
 #pragma unroll
           for (int t = 0; t < TC_TILES; ++t) {
-            const uint32_t col = COL_A + (as * TC_TILES + t) * C::ACT + h * KW;
+            const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + h * KW;
             if constexpr (GEN) {
               tc_st4(lane_addr + col, khi[t]);
               tc_st4(lane_addr + col + C::ACT / 2, klo[t]);
@@ -1270,12 +1163,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             }
           }
           }
-          if constexpr (DEFER) {
-            if (sb == 0 && g == 0) flush();
-          }
-          if (sb == 0 && (EARLY ? (g == 0) : (g == NG - 1))) {
+          if (EARLY ? (g == 0) : (g == NG - 1)) {
             if (tracer) TC_TRACE_P(it, 1);
-            if (!a_ready) mbar_wait_hybrid_sleep<PSBAX_AEMPTY_HINT>(&a_empty[ab], aph ^ 1, lane);
+            if (!a_ready) mbar_wait_hybrid_sleep<PSBAX_AEMPTY_HINT>(&a_empty[as], aph ^ 1, lane);
             if (tracer) TC_TRACE_P(it, 2);
             tc_fence_after();
           }
@@ -1285,7 +1175,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t) {
                 static_assert(C::INTERLEAVED && NG * C::WCOLS == C::KCOLS, "one k-step per producer warp");
-                const uint32_t col = COL_A + (as * TC_TILES + t) * C::ACT + h * C::A_KSTEP;
+                const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT + h * C::A_KSTEP;
                 const uint32_t u[16] = {s1[0][t][0], s1[0][t][1], s1[0][t][2], s1[0][t][3],
                                         s1[1][t][0], s1[1][t][1], s1[1][t][2], s1[1][t][3],
                                         s2[0][t][0], s2[0][t][1], s2[0][t][2], s2[0][t][3],
@@ -1305,7 +1195,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
             for (int gg = EARLY ? g : 0; gg <= g; ++gg)
 #pragma unroll
               for (int t = 0; t < TC_TILES; ++t) {
-                const uint32_t col = COL_A + (as * TC_TILES + t) * C::ACT +
+                const uint32_t col = TC_COL_A + (as * TC_TILES + t) * C::ACT +
                                      (C::INTERLEAVED ? h * C::A_KSTEP + gg * C::WCOLS : (h * NG + gg) * C::WCOLS);
                 if constexpr (BF) {
                   tc_st4(lane_addr + col, s1[gg][t]);
@@ -1325,26 +1215,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           for (int g = 0; g < NG; ++g) group(std::false_type{}, g);
         }
         }  // !kblk
-        }  // sub-blocks
         if constexpr (GEN) {  // done reading the streamed table block
           __syncwarp();
           if (lane == 0) mbar_arrive(&b_empty[bs]);
         }
-        if constexpr (DEFER) {
-          pend = ab;
-          if (tracer) TC_TRACE_P(it, 3);
-          if (tracer) TC_TRACE_P(it, 4);
-        } else {
-          tc_wait_st();
-          if (tracer) TC_TRACE_P(it, 3);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[ab]);
-          if (tracer) TC_TRACE_P(it, 4);
-        }
+        tc_wait_st();
+        if (tracer) TC_TRACE_P(it, 3);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0 && !PSBAX_EXP_FREERUN) mbar_arrive(&a_full[as]);
+        if (tracer) TC_TRACE_P(it, 4);
       }
     }
-    flush();
   } else if (warp >= TC_EPI_WARP0 && warp < TC_EPI_WARP0 + TC_NEPI) {
     // ================= epilogue =================
     const int q = warp & 3;
@@ -1354,46 +1236,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
     ls.init();
     uint32_t tl = 0;
     for (int pass = t0; pass < t1; ++pass, ++tl) {
-      const uint32_t buf = SD ? 0u : (tl & 1), dph = SD ? (tl & 1) : ((tl >> 1) & 1);
+      const uint32_t buf = tl & 1, dph = (tl >> 1) & 1;
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 0);
       if constexpr (PSBAX_TC_SLEEP_NS > 0) mbar_wait_hybrid_nanosleep<PSBAX_TC_SLEEP_NS>(&d_full[buf], dph, lane);
       else mbar_wait_hybrid_sleep<20000>(&d_full[buf], dph, lane);
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 1);
       tc_fence_after();
       const int r = q * 32 + lane;
-      if constexpr (SD) {
-        // single accumulator set: both tiles leave tensor memory first (one staging tile each), the accumulators
-        // are released, and only then do the reductions run
-#pragma unroll 1
-        for (int t = 0; t < TC_TILES; ++t) {
-          if (pass * TC_TILES + t < a.ntiles) {
-            float* so = sOut + t * (TN * OUT_LD);
-#pragma unroll 1
-            for (int c = 0; c < TN / 16; ++c) {
-              uint32_t u[16];
-              tc_ld16(lane_addr + TC_COL_D + t * TN + c * 16, u);
-              tc_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) so[(c * 16 + j) * OUT_LD + r] = __uint_as_float(u[j]);
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&d_empty[0]);
-        if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 2);
-        asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
-#pragma unroll 1
-        for (int t = 0; t < TC_TILES; ++t) {
-          const int tile = pass * TC_TILES + t;
-          if (tile < a.ntiles && !PSBAX_EXP_NOEPI) {
-            const float* so = sOut + t * (TN * OUT_LD);
-            if constexpr (EPI == EPI_LEVELSET) epilogue_levelset_reg<TC_NEPI>(a, so, ls, tile * TM, s0, etid);
-            else epilogue_tile<EPI, TC_NEPI>(a, so, e, tile * TM, s0, etid);
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");  // staging tiles free for the next pass
-      } else {
 #pragma unroll 1
       for (int t = 0; t < TC_TILES; ++t) {
         const int tile = pass * TC_TILES + t;
@@ -1419,7 +1268,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           else epilogue_tile<EPI, TC_NEPI>(a, sOut, e, tile * TM, s0, etid);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_NEPI * 32) : "memory");
-      }
       }
       if (warp == TC_EPI_WARP0 && lane == 0) TC_TRACE(2, tl, 3);
     }
