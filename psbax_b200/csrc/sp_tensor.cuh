@@ -736,8 +736,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_shared_tensor(const __grid_co
           const bool kblk = BF && kb >= nkb_r;
           const uint32_t fb = kblk ? ftbytes / 2 : ftbytes;
           const size_t frow = kblk ? (size_t)lay.kk0 + (size_t)(kb - nkb_r) * KF : (size_t)kb * TKB;
-#if PSBAX_EXP_NOCOPY  // what-if build (wrong results): the operand stream is not read at all
-          mbar_arrive_expect_tx(&b_full[bs], (GEN ? fb : 0u));
+#if PSBAX_EXP_NOCOPY  // what-if build (wrong results): the operand stream is not read at all (1), or only its
+          // first NSB blocks, which then stay in the ring as realistic non-zero operands (2)
+          if (PSBAX_EXP_NOCOPY == 2 && it < (uint32_t)NSB) {
+            mbar_arrive_expect_tx(&b_full[bs], C::BBYTES + (GEN ? fb : 0u));
+            bulk_g2s(sB + bs * STAGE, gB + (size_t)kb * C::BBYTES, C::BBYTES, &b_full[bs]);
+          } else {
+            mbar_arrive_expect_tx(&b_full[bs], (GEN ? fb : 0u));
+          }
 #else
           mbar_arrive_expect_tx(&b_full[bs], C::BBYTES + (GEN ? fb : 0u));
           bulk_g2s(sB + bs * STAGE, gB + (size_t)kb * C::BBYTES, C::BBYTES, &b_full[bs]);
