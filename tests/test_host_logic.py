@@ -365,3 +365,31 @@ def test_subset_select_class_multiplicative_golden(golden):
         assert exe_path.idxes == golden[pre + "idxes"].tolist()
         assert list(labels) == golden[pre + "labels"].tolist()
         np.testing.assert_allclose(exe_path.values, golden[pre + "values"], atol=1e-12)
+
+
+def test_bench_roofline_line_is_consistent():
+    """bench.py's roofline object: `frac` = roofline time of the binding pipe / kernel time against the BURST bf16
+    peak; `frac_vs_sustained_peak` = the same against MEASURED_PEAKS.json's sustained figure; every workload names
+    its binding pipe among tensor / MUFU / FFMA / HBM with the per-candidate counts of SURVEY.md section 8d."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    pk = bench.load_peaks()
+    for wl, eng in (("c2", "tensor_bf16x3"), ("c3", "tensor_bf16x3_proj"), ("c4", "tensor_bf16x3_proj"),
+                    ("c5", "tensor_bf16x3_proj")):
+        w = bench.WORKLOADS[wl]
+        r = bench.roofline(wl, eng, 8.0e-3, w["N"], wl == "c2")
+        assert r["bound"] in ("tensor", "mufu", "ffma", "hbm")
+        assert math.isclose(r["frac"], r["roofline_ms"] / r["kernel_ms"], rel_tol=1e-12)
+        assert math.isclose(r["roofline_ms"], max(r["pipes_ms"].values()), rel_tol=1e-12)
+        assert math.isclose(r["achieved"], r["frac"] * r["peak"], rel_tol=1e-12)
+        if r["bound"] == "tensor" and pk.get("bf16_tflops_sustained"):
+            assert math.isclose(r["frac_vs_sustained_peak"],
+                                r["frac"] * pk["bf16_tflops"] / pk["bf16_tflops_sustained"], rel_tol=1e-9)
+        else:
+            assert r["frac_vs_sustained_peak"] is None or r["bound"] == "tensor"
+    c2 = bench.roofline("c2", "tensor_bf16x3", 8.0e-3, bench.WORKLOADS["c2"]["N"], True)
+    assert c2["algorithmic"]["contraction_flop_per_candidate"] == 2 * (1000 + 64) * 64  # DESIGN.md section 4
+    assert c2["bound"] == "tensor"
